@@ -1,0 +1,150 @@
+/* mcm_b200 -- C ABI of the B200-native MCM scoring path.
+ *
+ * Drop-in boundary for ONE hot path of deeplearning-wisc/MCM:
+ *
+ *     CLIP ViT image-encoder forward -> L2-normalise -> cosine vs pre-encoded prompt bank
+ *     -> softmax(./T) -> max            (reference: utils/detection_util.py:209-249,
+ *                                        get_ood_scores_clip; the arithmetic it delegates to is
+ *                                        transformers.models.clip.modeling_clip, "HF:" below)
+ *
+ * The reference is pure Python and has no FFI; its seam for this path is the Python function
+ * `get_ood_scores_clip(args, net, loader, test_labels)` and the duck-typed `net`
+ * (`.get_image_features(pixel_values=)`).  `mcm_b200/detection_util.py` and `mcm_b200/engine.py`
+ * re-create those two seams on top of the entry points below through ctypes.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, a raw `cudaStream_t` passed as `void*`.
+ *   - every function returns 0 on success, a non-zero MCM_E* code on failure; the text of the last
+ *     failure is available from mcm_last_error(handle) (or mcm_last_error(NULL) for mcm_create).
+ *   - a handle is bound to one CUDA device and is NOT thread-safe (the reference drives one device
+ *     from one Python thread, eval_ood_detection.py:57-58).
+ *   - device work is enqueued on the caller's stream and is asynchronous; the caller synchronises
+ *     when it reads the scores.  Nothing is allocated inside mcm_score / mcm_image_features.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MCM_B200_H_
+#define MCM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCM_ABI_VERSION 1
+
+enum {
+    MCM_OK = 0,
+    MCM_EINVAL = 1,     /* bad argument (shape, range, NULL)                    */
+    MCM_ESTATE = 2,     /* call order: weights missing, bank not set, ...       */
+    MCM_ECUDA = 3,      /* a CUDA runtime / driver call failed                  */
+    MCM_ENOMEM = 4,
+    MCM_EUNSUPPORTED = 5 /* shape outside what the sm_100a kernels are built for */
+};
+
+/* Reduction applied to the [b,K] cosine logits; mirrors `args.score`
+ * (eval_ood_detection.py:36-37, utils/detection_util.py:233-248).  'maha' is a different method
+ * and not part of this path. */
+enum {
+    MCM_SCORE_MCM = 0,       /* -max_k softmax(z/T)          :236,248 */
+    MCM_SCORE_MAX_LOGIT = 1, /* -max_k z                     :234,248 */
+    MCM_SCORE_ENERGY = 2,    /* -T * logsumexp(z/T)          :239     */
+    MCM_SCORE_ENTROPY = 3,   /* entropy(softmax(z/T))        :243     */
+    MCM_SCORE_VAR = 4        /* -var_k softmax(z/T)          :246     */
+};
+
+/* Shape of the CLIP vision tower (HF CLIPVisionConfig + projection_dim,
+ * HF:configuration_clip.py; the reference picks it with --CLIP_ckpt, utils/train_eval_util.py:19-21). */
+typedef struct McmConfig {
+    int32_t image_size;  /* 224                                                     */
+    int32_t patch;       /* 16 (B/16), 14 (L/14), 32 (B/32)                         */
+    int32_t width;       /* hidden_size D; multiple of 128, <= 1024                 */
+    int32_t layers;      /* num_hidden_layers L                                     */
+    int32_t heads;       /* num_attention_heads H; D / H must be 64                 */
+    int32_t mlp;         /* intermediate_size F; multiple of 128                    */
+    int32_t proj;        /* projection_dim P; multiple of 4                         */
+    float eps;           /* layer_norm_eps (1e-5)                                   */
+    int32_t max_batch;   /* largest `b` a single mcm_score call will be given       */
+    int32_t device;      /* CUDA ordinal                                            */
+} McmConfig;
+
+typedef struct McmHandle McmHandle;
+
+/* Allocate packed-weight storage, the activation workspace for `max_batch` images and the TMA
+ * descriptors on `cfg->device`.  Replaces the model half of set_model_clip
+ * (utils/train_eval_util.py:15-26: CLIPModel.from_pretrained(...).cuda()). */
+int mcm_create(const McmConfig* cfg, McmHandle** out);
+void mcm_destroy(McmHandle* h);
+const char* mcm_last_error(const McmHandle* h);
+
+/* Hand one fp32 tensor of the HuggingFace CLIPModel state_dict to the engine, by its HF key
+ * (SURVEY.md 8b "Weights in"; e.g. "vision_model.encoder.layers.3.mlp.fc1.weight").  `data` may be
+ * a host or a device pointer (cudaMemcpyDefault); `numel` must match the configured shape.  Keys
+ * that are not part of the vision path (text tower, logit_scale, position_ids) are ignored and
+ * reported through *used = 0.  Replaces CLIPModel.load_state_dict for this path. */
+int mcm_load_weight(McmHandle* h, const char* hf_key, const float* data, int64_t numel, int32_t* used);
+
+/* Verify that every tensor of the vision path arrived and convert/pack them for the kernels
+ * (bf16 GEMM operands, fused QKV weight, padded patch filter).  Must precede any compute call. */
+int mcm_finalize_weights(McmHandle* h);
+
+/* Install the pre-encoded prompt bank: `bank` is [K,P] fp32 (host or device), one row per entry
+ * of `test_labels`.  Rows are L2-normalised on the device exactly like
+ * utils/detection_util.py:231 unless `already_unit` is non-zero.  The bank is copied. */
+int mcm_set_text_bank(McmHandle* h, const float* bank, int32_t K, int32_t already_unit);
+
+/* net.get_image_features(pixel_values=images)  (HF:829-863; called at utils/detection_util.py:225).
+ * images_dev: [b,3,image_size,image_size] fp32 NCHW on the device, already CLIP-normalised.
+ * feats_dev : [b,P] fp32, the un-normalised projected features. */
+int mcm_image_features(McmHandle* h, const float* images_dev, int32_t b, float* feats_dev, void* stream);
+
+/* One batch of utils/detection_util.py:225-248 with the bank pre-encoded:
+ * scores_dev[i] = reduce_k(normalise(features_i) . bank_k), `score_kind` one of MCM_SCORE_*.
+ * T follows args.T (eval_ood_detection.py:31; an int there, any positive float here). */
+int mcm_score(McmHandle* h, const float* images_dev, int32_t b, float T, int32_t score_kind, float* scores_dev,
+              void* stream);
+
+/* Whole stream of the loop at utils/detection_util.py:220-249 from HOST memory: n images are cut
+ * into batches of `batch` (<= max_batch), copied host->device on a copy stream while the previous
+ * batch is scored, and the n scores are copied back.  Synchronous.  images_host should be pinned
+ * for full copy bandwidth but need not be. */
+int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int32_t batch, float T,
+                          int32_t score_kind, float* scores_host);
+
+/* Number of kernels of this library launched on the handle's device since the last reset
+ * (bench.py reports it as `gpu_launches`). */
+int64_t mcm_launch_count(const McmHandle* h);
+void mcm_reset_launch_count(McmHandle* h);
+
+/* Algorithmic FLOPs per image of the configured tower with a K-row bank. */
+double mcm_flops_per_image(const McmConfig* cfg, int32_t K);
+
+int32_t mcm_abi_version(void);
+
+/* ---- per-kernel entry points (used by tests/ to check every kernel against a torch fp32
+ *      reference of the same op, and by bench.py for the per-kernel roofline).  All pointers are
+ *      device pointers; all calls are asynchronous on `stream`. ---- */
+
+/* out = epilogue(A[M,K] @ W[N,K]^T): A, W bf16 row-major.
+ * epi 0: out bf16 = acc + bias            1: out bf16 = quick_gelu(acc + bias)
+ * epi 2: out f32  = resid + acc + bias    (resid may alias out) */
+int mcm_dbg_gemm(McmHandle* h, const void* a_bf16, const void* w_bf16, const float* bias, const float* resid,
+                 void* out, int32_t M, int32_t N, int32_t K, int32_t epi, void* stream);
+/* nn.LayerNorm over the last dim (HF:359-361): x f32 [M,D] -> out bf16 (out_bf16 != 0) or f32. */
+int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* gamma, const float* beta, void* out, int32_t M,
+                      int32_t D, float eps, int32_t out_bf16, void* stream);
+/* softmax(q k^T / 8) v per (image, head) (HF:261-279,318-331): qkv bf16 [b*S, 3*H*64] -> o bf16 [b*S, H*64]. */
+int mcm_dbg_attention(McmHandle* h, const void* qkv_bf16, void* o_bf16, int32_t b, int32_t S, int32_t H,
+                      void* stream);
+/* CLS pool + post_layernorm + visual_projection (HF:685-686,860-861) + the scoring tail.
+ * x f32 [b*S, D] (row b*S is the CLS token); feats (may be NULL) [b,P]; scores (may be NULL) [b]. */
+int mcm_dbg_tail(McmHandle* h, const float* x, int32_t b, float T, int32_t score_kind, float* feats, float* scores,
+                 void* stream);
+/* embeddings + pre_layrnorm (HF:202-218,677): images f32 [b,3,H,W] -> x f32 [b*S, D]. */
+int mcm_dbg_embed(McmHandle* h, const float* images, int32_t b, float* x, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCM_B200_H_ */
