@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the MCM hot path: images/sec MCM-scored (ViT-B/16, K = 1000 prompt bank).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path (CLIP ViT image encoder -> normalise -> cosine vs the
+pre-encoded bank -> softmax/T -> max) over one batch of `--batch` synthetic 224x224 images.
+
+* ``value``: whole-job images/sec with the inputs already resident in HBM; timed with CUDA events
+  on the launching stream, barrier + synchronize on both sides, max over ranks.  The resident
+  input pool is larger than L2 and rotates, so no step re-reads cached pixels.
+* ``e2e``: the same metric through the C-ABI host entry point (``mcm_score_stream_host``) with
+  pinned HOST buffers: H2D copy of every batch and D2H of the scores inside the timed region.
+* ``roofline``: the dominant kernel (the tcgen05 GEMM: 96 % of the FLOPs) -- algorithmic GEMM
+  FLOPs of a step / the summed duration of its GEMM launches, measured live with CUDA events in
+  a separate instrumented pass, against the measured bf16 peak in MEASURED_PEAKS.json.
+* ``cpu_baseline``: the CPU oracle (a torch-CPU port of the reference path, bank pre-encoded)
+  timed on this box's host cores on a bounded sample (rank 0, N = 1 only).
+* ``--impl reference``: the reference's CPU implementation of the path on the host cores
+  (oracle port; /root/reference cannot travel to the GPU box), same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec MCM-scored (ViT-B/16, K=1000)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU (multiple of 128 keeps M = b*197 a multiple of 128)")
+    ap.add_argument("--model", default="ViT-B/16")
+    ap.add_argument("--K", type=int, default=1000)
+    ap.add_argument("--pool", type=int, default=4, help="distinct resident batches (pool * batch * 602 KB > L2)")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="images of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(cfg, sd, bank, n_images, repeats=1):
+    """Oracle (torch-CPU port of the reference loop, bank pre-encoded) on the host cores."""
+    from mcm_b200 import synth
+    from oracle import clip_mcm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs = torch.from_numpy(synth.synth_images(n_images, 1234))
+    bank_t = torch.from_numpy(bank)
+    O.ood_scores(imgs[: min(8, n_images)], sd, cfg, bank_t, batch=8)      # warm-up (thread pools, allocator)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.ood_scores(imgs, sd, cfg, bank_t, T=1, score="MCM", batch=min(n_images, 32))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_images / best, best
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU path for the same metric/config (rank 0 only)."""
+    if rank != 0:
+        return
+    from mcm_b200 import synth
+    cfg = synth.CFGS[args.model]
+    sd = synth.synth_vision_state_dict(cfg, 5)
+    bank = synth.synth_unit_bank(args.K, cfg.proj, 3)
+    per_step = 16          # bounded sample per step: ~1 s of CPU work
+    from oracle import clip_mcm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs = torch.from_numpy(synth.synth_images(per_step, 1234))
+    bank_t = torch.from_numpy(bank)
+    for _ in range(args.warmup):
+        O.ood_scores(imgs, sd, cfg, bank_t, batch=per_step)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.ood_scores(imgs, sd, cfg, bank_t, T=1, score="MCM", batch=per_step)
+    dt = time.perf_counter() - t0
+    v = steps * per_step / dt
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CLIP {args.model} image encoder + MCM scoring, K={args.K} prompt bank, "
+                                   f"synthetic 224x224 stream", "batch_per_step": per_step, "device": "host CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} steps x {per_step} images, torch-CPU fp32 oracle port of "
+                                       f"utils/detection_util.py:209-249 + HF CLIP (bank pre-encoded), {cores} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback (use --impl reference for the CPU baseline)")
+
+    import torch.distributed as dist
+    from mcm_b200 import synth
+    from mcm_b200.engine import McmEngine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.CFGS[args.model]
+    B, K = args.batch, args.K
+    sd = synth.synth_vision_state_dict(cfg, 5)
+    bank = synth.synth_unit_bank(K, cfg.proj, 3)
+    eng = McmEngine.from_state_dict(sd, cfg, max_batch=B, device=local_rank)
+    eng.set_text_bank(bank, already_unit=True)
+
+    # resident input pool (> L2): generated on the device, "already CLIP-normalised" N(0,1) pixels
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    pool = [torch.randn((B, 3, cfg.image_size, cfg.image_size), device=dev, generator=g) for _ in range(args.pool)]
+    scores = torch.empty((max(args.steps, 1) * B,), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i, out):
+        eng.score(pool[i % len(pool)], T=1.0, score="MCM", out=out)
+
+    for i in range(args.warmup):
+        step(i, scores[:B])
+    barrier()
+
+    # ---------------- device-resident timed region ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i, scores[i * B:(i + 1) * B])
+    if world > 1:   # the path's one collective: collate the per-rank scores of the stream
+        recv = torch.empty((world * args.steps * B,), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(recv, scores[: args.steps * B])
+    ev1.record(stream)
+    barrier()
+    launches = eng.launch_count
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.steps * B / (ms * 1e-3)
+
+    # ---------------- end-to-end: host buffers through the C-ABI stream entry point ----------------
+    host = torch.empty((len(pool) * B, 3, cfg.image_size, cfg.image_size), dtype=torch.float32).pin_memory()
+    for j, p in enumerate(pool):
+        host[j * B:(j + 1) * B].copy_(p)
+    eng.score_stream_host(host[: 2 * B], batch=B)       # warm-up (allocates the staging buffers)
+    barrier()
+    n_e2e = args.steps * B
+    t0 = time.perf_counter()
+    done = 0
+    while done < n_e2e:
+        cur = min(n_e2e - done, host.shape[0])
+        eng.score_stream_host(host[:cur], batch=B)
+        done += cur
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e / float(te.item())
+
+    # ---------------- per-kernel durations (instrumented pass, CUDA events on the launching stream) ----------------
+    eng.profile(True)
+    prof_steps = max(3, min(args.steps, 6))
+    for i in range(prof_steps):
+        step(i, scores[:B])
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+    S, D, F, L, Np = cfg.seq, cfg.width, cfg.mlp, cfg.layers, cfg.seq - 1
+    gemm_flops = B * (2.0 * Np * (3 * cfg.patch ** 2) * D + L * (8.0 * S * D * D + 4.0 * S * D * F))
+    gemm_kinds = ["gemm_patch", "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2"]
+    gemm_ms = sum(prof[k][0] for k in gemm_kinds) / prof_steps
+    gemm_launches = sum(prof[k][1] for k in gemm_kinds) // prof_steps
+    pk = peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] // prof_steps} for k, v in prof.items() if v[1]}
+    flops_img = eng.flops_per_image(K)
+    step_tf = (value / world) * flops_img / 1e12
+
+    line = None
+    if rank == 0:
+        cpu_base = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, secs = cpu_reference_rate(cfg, sd, bank, args.cpu_sample)
+            cores = os.cpu_count() or 1
+            cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_sample} images of the same workload ({secs:.1f} s), torch-CPU fp32 oracle "
+                                  f"port of utils/detection_util.py:209-249 + HF CLIP, bank pre-encoded, {cores} threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"CLIP {args.model} image encoder + MCM scoring, K={K} prompt bank (BASELINE "
+                                   f"configs[2] shape), synthetic 224x224 fp32 stream, random-init weights",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": f"resident input pool {len(pool)} x {B * 3 * 224 * 224 * 4 / 1e6:.0f} MB rotates (> 126 MB L2)",
+                       "precision": "bf16 tensor-core operands, fp32 accumulate / residual / LayerNorm / softmax / tail"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
+                    "d2h_bytes_per_step": B * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all GEMMs of a step)",
+                         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tf_sustained"], "traffic": None,
+                         "peak_source": f"bf16_tflops_sustained, {pk['source']}",
+                         "launches_per_step": int(gemm_launches), "gemm_ms_per_step": gemm_ms,
+                         "step_tflops": step_tf, "step_frac": step_tf / pk["tf_sustained"]},
+            "kernels": kernels,
+            "flops_per_image": flops_img,
+        }
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

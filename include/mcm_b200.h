@@ -117,6 +117,18 @@ int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int
 int64_t mcm_launch_count(const McmHandle* h);
 void mcm_reset_launch_count(McmHandle* h);
 
+/* Optional per-launch timing for bench.py's roofline: while enabled, every kernel launch of a
+ * forward is bracketed by CUDA events on the launching stream.  mcm_profile_read synchronises the
+ * device and returns accumulated milliseconds and launch counts per kernel kind (arrays of
+ * MCM_PROF_KINDS entries); `reset` clears the accumulators. */
+enum {
+    MCM_PROF_PATCHIFY = 0, MCM_PROF_GEMM_PATCH = 1, MCM_PROF_EMBED_FINISH = 2, MCM_PROF_GEMM_QKV = 3,
+    MCM_PROF_ATTENTION = 4, MCM_PROF_GEMM_OUT = 5, MCM_PROF_LAYERNORM = 6, MCM_PROF_GEMM_FC1 = 7,
+    MCM_PROF_GEMM_FC2 = 8, MCM_PROF_TAIL = 9, MCM_PROF_GEMM_OTHER = 10, MCM_PROF_KINDS = 11
+};
+int mcm_profile_enable(McmHandle* h, int32_t on);
+int mcm_profile_read(McmHandle* h, double* ms, int64_t* counts, int32_t reset);
+
 /* Algorithmic FLOPs per image of the configured tower with a K-row bank. */
 double mcm_flops_per_image(const McmConfig* cfg, int32_t K);
 

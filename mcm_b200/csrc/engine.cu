@@ -1,0 +1,790 @@
+// mcm_b200 engine: the C ABI of include/mcm_b200.h on top of the sm_100a kernels in this directory.
+//
+// One handle = one CLIP vision tower resident on one B200: bf16 GEMM weights (fused QKV), fp32
+// biases / LayerNorm / embeddings / projection / prompt bank, the activation workspace for
+// `max_batch` images and the TMA descriptors of every GEMM operand.  A forward is a fixed sequence
+// of launches on the caller's stream; nothing is allocated after mcm_create.
+//
+// Path per batch (reference: utils/detection_util.py:225-248 -> HF modeling_clip.py:829-863):
+//   patchify -> patch GEMM(+pos) -> embed_finish(CLS, pre-LN, LN1) ->
+//   L x [ QKV GEMM -> attention -> out-proj GEMM(+residual) -> LN2 -> fc1 GEMM(+quick_gelu)
+//         -> fc2 GEMM(+residual) -> LN1 of the next layer ] -> tail (post-LN, projection, MCM score)
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcm_b200.h"
+#include "attention_mma.cuh"
+#include "gemm_tcgen05.cuh"
+#include "rowwise.cuh"
+#include "tail.cuh"
+
+using namespace mcm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+struct LayerWeights {
+    __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+    float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+    CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+};
+
+}  // namespace
+
+struct McmHandle {
+    McmConfig cfg{};
+    int G = 0, Np = 0, S = 0, D = 0, H = 0, F = 0, P = 0, L = 0, Kp = 0, Kpatch = 0;
+    int num_sms = 0;
+    int64_t m_pad = 0, mp_pad = 0;  // padded token rows / patch rows for max_batch
+    std::string err;
+
+    // weights
+    __nv_bfloat16* wpatch = nullptr;  // [D, Kp]
+    float *cls = nullptr, *pos = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr;
+    float* wproj = nullptr;  // [P, D]
+    std::vector<LayerWeights> layers;
+    CUtensorMap tm_wpatch;
+    std::vector<uint8_t> loaded;  // one flag per expected tensor
+    std::vector<std::string> expected;
+    bool finalized = false;
+    float* stage = nullptr;  // fp32 staging for one weight tensor
+    size_t stage_elems = 0;
+
+    // prompt bank
+    float* bank = nullptr;
+    int K = 0;
+
+    // workspace
+    __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
+    float* x = nullptr;
+    CUtensorMap tm_patches, tm_xn, tm_attn, tm_hid;
+
+    // host-stream path
+    float* img_buf[2] = {nullptr, nullptr};
+    float* scores_buf = nullptr;
+    int64_t scores_cap = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+    int64_t launches = 0;
+
+    // optional per-launch timing (mcm_profile_*): events bracket every launch of a forward
+    bool prof_on = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[MCM_PROF_KINDS] = {0};
+    int64_t prof_n[MCM_PROF_KINDS] = {0};
+};
+
+namespace {
+
+int fail(McmHandle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+cudaEvent_t prof_event(McmHandle* h) {
+    if (!h->prof_pool.empty()) {
+        cudaEvent_t e = h->prof_pool.back();
+        h->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// RAII bracket: records an event pair around one launch when profiling is on
+struct ProfScope {
+    McmHandle* h;
+    cudaStream_t st;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(McmHandle* h_, int kind_, cudaStream_t st_) : h(h_), st(st_), kind(kind_) {
+        if (h->prof_on) {
+            a = prof_event(h);
+            b = prof_event(h);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ProfScope() {
+        if (a) {
+            cudaEventRecord(b, st);
+            h->prof_recs.push_back({kind, a, b});
+        }
+    }
+};
+
+#define MCM_CUDA(h, call)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(h, MCM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int make_tmap(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
+                    (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return MCM_OK;
+}
+
+inline int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+template <int BN, int EPI>
+int launch_gemm_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    static bool attr_done = false;  // per instantiation; one device per process in practice
+    auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+    if (!attr_done) {
+        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+        attr_done = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, p);
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+// C[M, N] = A[M, K] W[N, K]^T with fused epilogue.  M rows valid; A's tensor map covers >= ceil(M/128)*128 rows.
+int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi,
+                const float* bias, void* out, const float* resid, const float* pos, int np, int seq, cudaStream_t st) {
+    if (M <= 0) return MCM_OK;
+    if (N % 128 != 0 || K % kGemmBlockK != 0)
+        return fail(h, MCM_EUNSUPPORTED, "GEMM shape N=%d (multiple of 128) K=%d (multiple of 64) unsupported", N, K);
+    const int bn = gemm_block_n(N);
+    GemmParams p{};
+    p.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    p.n_tiles = N / bn;
+    p.k_blocks = K / kGemmBlockK;
+    p.m_valid = M;
+    p.ldo = N;
+    p.bias = bias;
+    p.out = out;
+    p.resid = resid;
+    p.pos = pos;
+    p.np = np;
+    p.seq = seq;
+    ProfScope prof(h, prof_kind, st);
+#define MCM_GEMM_CASE(BN, E) \
+    if (bn == BN && epi == E) return launch_gemm_t<BN, E>(h, ta, tb, p, st);
+    MCM_GEMM_CASE(256, EPI_BIAS_BF16)
+    MCM_GEMM_CASE(256, EPI_BIAS_QGELU_BF16)
+    MCM_GEMM_CASE(256, EPI_BIAS_RESID_F32)
+    MCM_GEMM_CASE(256, EPI_POS_F32)
+    MCM_GEMM_CASE(128, EPI_BIAS_BF16)
+    MCM_GEMM_CASE(128, EPI_BIAS_QGELU_BF16)
+    MCM_GEMM_CASE(128, EPI_BIAS_RESID_F32)
+    MCM_GEMM_CASE(128, EPI_POS_F32)
+#undef MCM_GEMM_CASE
+    return fail(h, MCM_EINVAL, "unknown GEMM epilogue %d", epi);
+}
+
+template <typename F>
+int dispatch_vec(McmHandle* h, int D, F&& f) {
+    switch (D / 128) {
+        case 1: return f(std::integral_constant<int, 1>{});
+        case 2: return f(std::integral_constant<int, 2>{});
+        case 3: return f(std::integral_constant<int, 3>{});
+        case 4: return f(std::integral_constant<int, 4>{});
+        case 5: return f(std::integral_constant<int, 5>{});
+        case 6: return f(std::integral_constant<int, 6>{});
+        case 7: return f(std::integral_constant<int, 7>{});
+        case 8: return f(std::integral_constant<int, 8>{});
+        default: return fail(h, MCM_EUNSUPPORTED, "width %d unsupported (multiple of 128, <= 1024)", D);
+    }
+}
+
+int launch_layernorm(McmHandle* h, const float* x, const float* g, const float* b, void* out, int M, int D, float eps,
+                     bool out_bf16, cudaStream_t st) {
+    if (M <= 0) return MCM_OK;
+    if (D % 128 != 0) return fail(h, MCM_EUNSUPPORTED, "LayerNorm width %d is not a multiple of 128", D);
+    const int grid = (M + (kRowThreads / 32) - 1) / (kRowThreads / 32);
+    ProfScope prof(h, MCM_PROF_LAYERNORM, st);
+    int rc = dispatch_vec(h, D, [&](auto vec) {
+        constexpr int V = decltype(vec)::value;
+        if (out_bf16)
+            layernorm_kernel<V, true><<<grid, kRowThreads, 0, st>>>(x, g, b, out, M, eps);
+        else
+            layernorm_kernel<V, false><<<grid, kRowThreads, 0, st>>>(x, g, b, out, M, eps);
+        return MCM_OK;
+    });
+    if (rc) return rc;
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+int launch_attention(McmHandle* h, const __nv_bfloat16* qkv, __nv_bfloat16* out, int b, int S, int H, cudaStream_t st) {
+    if (b <= 0) return MCM_OK;
+    const int keys_pad = (S + 15) / 16 * 16;
+    const size_t smem = static_cast<size_t>(2) * keys_pad * kAttnLd * sizeof(__nv_bfloat16);
+    if (smem > 200 * 1024) return fail(h, MCM_EUNSUPPORTED, "sequence length %d too long for the attention kernel", S);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        MCM_CUDA(h, cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int mtiles = (S + 15) / 16;
+    int nwarps = (mtiles + 1) / 2;
+    if (nwarps > 9) nwarps = 9;
+    if (nwarps < 1) nwarps = 1;
+    const float scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
+    ProfScope prof(h, MCM_PROF_ATTENTION, st);
+    attention_mma_kernel<<<b * H, nwarps * 32, smem, st>>>(qkv, out, S, H, keys_pad, scale_log2e);
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+int launch_tail(McmHandle* h, const float* x, int b, float T, int kind, float* feats, float* scores, cudaStream_t st) {
+    if (b <= 0) return MCM_OK;
+    const int K = scores ? h->K : 0;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(kTailImgs) * (h->D + h->P + K) + 8 + kTailImgs);
+    if (smem > 220 * 1024) return fail(h, MCM_EUNSUPPORTED, "prompt bank with K=%d rows does not fit the tail kernel", K);
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        MCM_CUDA(h, cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int grid = (b + kTailImgs - 1) / kTailImgs;
+    ProfScope prof(h, MCM_PROF_TAIL, st);
+    tail_kernel<<<grid, kTailThreads, smem, st>>>(x, h->S, h->D, h->P, K, b, h->post_g, h->post_b, h->cfg.eps, h->wproj,
+                                                  h->bank, T, kind, feats, scores);
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
+    {
+        ProfScope prof(h, MCM_PROF_PATCHIFY, st);
+        patchify_kernel<<<b * h->G, 256, 0, st>>>(images, h->patches, h->G, h->cfg.patch, h->Kp);
+    }
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    int rc = launch_gemm(h, MCM_PROF_GEMM_PATCH, h->tm_patches, h->tm_wpatch, b * h->Np, h->D, h->Kp, EPI_POS_F32, nullptr, h->x, nullptr,
+                         h->pos, h->Np, h->S, st);
+    if (rc) return rc;
+    const int M = b * h->S;
+    const int grid = (M + (kRowThreads / 32) - 1) / (kRowThreads / 32);
+    const LayerWeights& l0 = h->layers[0];
+    ProfScope prof(h, MCM_PROF_EMBED_FINISH, st);
+    rc = dispatch_vec(h, h->D, [&](auto vec) {
+        constexpr int V = decltype(vec)::value;
+        embed_finish_kernel<V><<<grid, kRowThreads, 0, st>>>(h->x, h->xn, h->cls, h->pos, h->pre_g, h->pre_b, l0.ln1g,
+                                                              l0.ln1b, M, h->S, h->cfg.eps);
+        return MCM_OK;
+    });
+    if (rc) return rc;
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+// embeddings + encoder; leaves the fp32 residual stream of the last layer in h->x
+int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st) {
+    int rc = launch_embed(h, images, b, st);
+    if (rc) return rc;
+    const int M = b * h->S, D = h->D, F = h->F;
+    for (int i = 0; i < h->L; ++i) {
+        const LayerWeights& w = h->layers[i];
+        // xn = LN1(x) is already in place (embed_finish for layer 0, end of the previous layer otherwise)
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xn, w.tm_wqkv, M, 3 * D, D, EPI_BIAS_BF16, w.bqkv, h->qkv, nullptr, nullptr, 0, 0, st))) return rc;
+        if ((rc = launch_attention(h, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32, w.bo, h->x, h->x, nullptr, 0, 0, st))) return rc;
+        if ((rc = launch_layernorm(h, h->x, w.ln2g, w.ln2b, h->xn, M, D, h->cfg.eps, true, st))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, M, F, D, EPI_BIAS_QGELU_BF16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, EPI_BIAS_RESID_F32, w.b2, h->x, h->x, nullptr, 0, 0, st))) return rc;
+        if (i + 1 < h->L) {
+            const LayerWeights& n = h->layers[i + 1];
+            if ((rc = launch_layernorm(h, h->x, n.ln1g, n.ln1b, h->xn, M, D, h->cfg.eps, true, st))) return rc;
+        }
+    }
+    return MCM_OK;
+}
+
+int check_ready(McmHandle* h, int b, bool need_bank) {
+    if (!h) return MCM_EINVAL;
+    if (!h->finalized) return fail(h, MCM_ESTATE, "weights are not finalized (call mcm_finalize_weights)");
+    if (need_bank && h->K <= 0) return fail(h, MCM_ESTATE, "text bank is not set (call mcm_set_text_bank)");
+    if (b < 0 || b > h->cfg.max_batch) return fail(h, MCM_EINVAL, "batch %d outside [0, max_batch=%d]", b, h->cfg.max_batch);
+    return MCM_OK;
+}
+
+template <typename T>
+int dev_alloc(McmHandle* h, T** p, size_t n, bool zero) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 16);
+    if (e != cudaSuccess) return fail(h, MCM_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    if (zero) {
+        e = cudaMemset(q, 0, n * sizeof(T));
+        if (e != cudaSuccess) return fail(h, MCM_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    *p = static_cast<T*>(q);
+    return MCM_OK;
+}
+
+// where one HF tensor goes
+struct Dest {
+    float* f32 = nullptr;            // fp32 destination, or
+    __nv_bfloat16* bf16 = nullptr;   // bf16 destination (converted)
+    int64_t rows = 0;
+    int cols = 0, dst_ld = 0;
+    int slot = -1;
+};
+
+bool parse_layer_key(const char* key, int* layer, const char** rest) {
+    static const char* pre = "vision_model.encoder.layers.";
+    const size_t n = strlen(pre);
+    if (strncmp(key, pre, n) != 0) return false;
+    char* end = nullptr;
+    long v = strtol(key + n, &end, 10);
+    if (end == key + n || *end != '.') return false;
+    *layer = static_cast<int>(v);
+    *rest = end + 1;
+    return true;
+}
+
+// slot numbering: 0..7 globals, then 16 per layer
+enum { SLOT_CLS = 0, SLOT_PATCH, SLOT_POS, SLOT_PRE_G, SLOT_PRE_B, SLOT_POST_G, SLOT_POST_B, SLOT_PROJ, SLOT_GLOBALS };
+const char* kLayerNames[16] = {"layer_norm1.weight", "layer_norm1.bias", "layer_norm2.weight", "layer_norm2.bias",
+                               "self_attn.q_proj.weight", "self_attn.q_proj.bias", "self_attn.k_proj.weight",
+                               "self_attn.k_proj.bias", "self_attn.v_proj.weight", "self_attn.v_proj.bias",
+                               "self_attn.out_proj.weight", "self_attn.out_proj.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                               "mlp.fc2.weight", "mlp.fc2.bias"};
+
+bool resolve_key(McmHandle* h, const char* key, Dest* d) {
+    const int D = h->D, F = h->F, P = h->P;
+    auto f32 = [&](float* p, int64_t n, int slot) { d->f32 = p; d->rows = 1; d->cols = (int)n; d->slot = slot; return true; };
+    auto b16 = [&](__nv_bfloat16* p, int64_t rows, int cols, int ld, int slot) {
+        d->bf16 = p; d->rows = rows; d->cols = cols; d->dst_ld = ld; d->slot = slot; return true;
+    };
+    if (!strcmp(key, "vision_model.embeddings.class_embedding")) return f32(h->cls, D, SLOT_CLS);
+    if (!strcmp(key, "vision_model.embeddings.patch_embedding.weight")) return b16(h->wpatch, D, h->Kpatch, h->Kp, SLOT_PATCH);
+    if (!strcmp(key, "vision_model.embeddings.position_embedding.weight")) return f32(h->pos, (int64_t)h->S * D, SLOT_POS);
+    if (!strcmp(key, "vision_model.pre_layrnorm.weight")) return f32(h->pre_g, D, SLOT_PRE_G);
+    if (!strcmp(key, "vision_model.pre_layrnorm.bias")) return f32(h->pre_b, D, SLOT_PRE_B);
+    if (!strcmp(key, "vision_model.post_layernorm.weight")) return f32(h->post_g, D, SLOT_POST_G);
+    if (!strcmp(key, "vision_model.post_layernorm.bias")) return f32(h->post_b, D, SLOT_POST_B);
+    if (!strcmp(key, "visual_projection.weight")) return f32(h->wproj, (int64_t)P * D, SLOT_PROJ);
+    int li = 0;
+    const char* rest = nullptr;
+    if (!parse_layer_key(key, &li, &rest) || li < 0 || li >= h->L) return false;
+    LayerWeights& w = h->layers[li];
+    int which = -1;
+    for (int i = 0; i < 16; ++i)
+        if (!strcmp(rest, kLayerNames[i])) which = i;
+    if (which < 0) return false;
+    const int slot = SLOT_GLOBALS + li * 16 + which;
+    switch (which) {
+        case 0: return f32(w.ln1g, D, slot);
+        case 1: return f32(w.ln1b, D, slot);
+        case 2: return f32(w.ln2g, D, slot);
+        case 3: return f32(w.ln2b, D, slot);
+        case 4: return b16(w.wqkv, D, D, D, slot);
+        case 5: return f32(w.bqkv, D, slot);
+        case 6: return b16(w.wqkv + (size_t)D * D, D, D, D, slot);
+        case 7: return f32(w.bqkv + D, D, slot);
+        case 8: return b16(w.wqkv + (size_t)2 * D * D, D, D, D, slot);
+        case 9: return f32(w.bqkv + 2 * D, D, slot);
+        case 10: return b16(w.wo, D, D, D, slot);
+        case 11: return f32(w.bo, D, slot);
+        case 12: return b16(w.w1, F, D, D, slot);
+        case 13: return f32(w.b1, F, slot);
+        case 14: return b16(w.w2, D, F, F, slot);
+        case 15: return f32(w.b2, D, slot);
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mcm_abi_version(void) { return MCM_ABI_VERSION; }
+
+const char* mcm_last_error(const McmHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+double mcm_flops_per_image(const McmConfig* c, int32_t K) {
+    if (!c || c->patch <= 0) return 0.0;
+    const double G = c->image_size / c->patch, S = G * G + 1, D = c->width, F = c->mlp, P = c->proj, L = c->layers;
+    const double p2 = 3.0 * c->patch * c->patch;
+    return 2.0 * (S - 1) * p2 * D + L * (8.0 * S * D * D + 4.0 * S * D * F + 4.0 * S * S * D) + 2.0 * D * P + 2.0 * P * K;
+}
+
+int mcm_create(const McmConfig* cfg, McmHandle** out) {
+    if (!cfg || !out) return fail(nullptr, MCM_EINVAL, "mcm_create: NULL argument");
+    *out = nullptr;
+    if (cfg->patch <= 0 || cfg->image_size <= 0 || cfg->image_size % cfg->patch != 0 || (cfg->patch & 1))
+        return fail(nullptr, MCM_EINVAL, "image_size %d must be a multiple of an even patch size (%d)", cfg->image_size, cfg->patch);
+    if (cfg->width <= 0 || cfg->width % 128 != 0 || cfg->width > 1024)
+        return fail(nullptr, MCM_EUNSUPPORTED, "width %d must be a multiple of 128, at most 1024", cfg->width);
+    if (cfg->heads <= 0 || cfg->width != cfg->heads * 64)
+        return fail(nullptr, MCM_EUNSUPPORTED, "width / heads must be 64 (got %d / %d)", cfg->width, cfg->heads);
+    if (cfg->mlp <= 0 || cfg->mlp % 128 != 0) return fail(nullptr, MCM_EUNSUPPORTED, "mlp %d must be a multiple of 128", cfg->mlp);
+    if (cfg->proj <= 0 || cfg->proj % 4 != 0) return fail(nullptr, MCM_EUNSUPPORTED, "proj %d must be a multiple of 4", cfg->proj);
+    if (cfg->layers <= 0 || cfg->max_batch <= 0) return fail(nullptr, MCM_EINVAL, "layers and max_batch must be positive");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MCM_ECUDA, "no CUDA device available (%s); mcm_b200 has no CPU path", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MCM_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
+        return fail(nullptr, MCM_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MCM_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+                    prop.major, prop.minor);
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, MCM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    McmHandle* h = new McmHandle();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    h->G = cfg->image_size / cfg->patch;
+    h->Np = h->G * h->G;
+    h->S = h->Np + 1;
+    h->D = cfg->width;
+    h->H = cfg->heads;
+    h->F = cfg->mlp;
+    h->P = cfg->proj;
+    h->L = cfg->layers;
+    h->Kpatch = 3 * cfg->patch * cfg->patch;
+    h->Kp = (h->Kpatch + kGemmBlockK - 1) / kGemmBlockK * kGemmBlockK;
+    h->m_pad = (static_cast<int64_t>(cfg->max_batch) * h->S + 127) / 128 * 128;
+    h->mp_pad = (static_cast<int64_t>(cfg->max_batch) * h->Np + 127) / 128 * 128;
+    const int D = h->D, F = h->F;
+
+#define MCM_TRY(expr)               \
+    do {                            \
+        int rc__ = (expr);          \
+        if (rc__) {                 \
+            g_create_error = h->err; \
+            mcm_destroy(h);         \
+            return rc__;            \
+        }                           \
+    } while (0)
+
+    MCM_TRY(dev_alloc(h, &h->wpatch, (size_t)D * h->Kp, true));
+    MCM_TRY(dev_alloc(h, &h->cls, D, true));
+    MCM_TRY(dev_alloc(h, &h->pos, (size_t)h->S * D, true));
+    MCM_TRY(dev_alloc(h, &h->pre_g, D, true));
+    MCM_TRY(dev_alloc(h, &h->pre_b, D, true));
+    MCM_TRY(dev_alloc(h, &h->post_g, D, true));
+    MCM_TRY(dev_alloc(h, &h->post_b, D, true));
+    MCM_TRY(dev_alloc(h, &h->wproj, (size_t)h->P * D, true));
+    h->layers.resize(h->L);
+    for (auto& w : h->layers) {
+        MCM_TRY(dev_alloc(h, &w.wqkv, (size_t)3 * D * D, false));
+        MCM_TRY(dev_alloc(h, &w.wo, (size_t)D * D, false));
+        MCM_TRY(dev_alloc(h, &w.w1, (size_t)F * D, false));
+        MCM_TRY(dev_alloc(h, &w.w2, (size_t)D * F, false));
+        MCM_TRY(dev_alloc(h, &w.bqkv, (size_t)3 * D, false));
+        MCM_TRY(dev_alloc(h, &w.bo, D, false));
+        MCM_TRY(dev_alloc(h, &w.b1, F, false));
+        MCM_TRY(dev_alloc(h, &w.b2, D, false));
+        MCM_TRY(dev_alloc(h, &w.ln1g, D, false));
+        MCM_TRY(dev_alloc(h, &w.ln1b, D, false));
+        MCM_TRY(dev_alloc(h, &w.ln2g, D, false));
+        MCM_TRY(dev_alloc(h, &w.ln2b, D, false));
+        const uint32_t bnD = gemm_block_n(D), bn3D = gemm_block_n(3 * D), bnF = gemm_block_n(F);
+        MCM_TRY(make_tmap(h, &w.tm_wqkv, w.wqkv, 3 * D, D, bn3D));
+        MCM_TRY(make_tmap(h, &w.tm_wo, w.wo, D, D, bnD));
+        MCM_TRY(make_tmap(h, &w.tm_w1, w.w1, F, D, bnF));
+        MCM_TRY(make_tmap(h, &w.tm_w2, w.w2, D, F, bnD));
+    }
+    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D)));
+    h->loaded.assign(SLOT_GLOBALS + 16 * h->L, 0);
+    h->stage_elems = (size_t)std::max(std::max((size_t)F * D, (size_t)D * h->Kpatch), std::max((size_t)h->S * D, (size_t)h->P * D));
+    MCM_TRY(dev_alloc(h, &h->stage, h->stage_elems, false));
+
+    // activation workspace (padding rows are zeroed once and only ever read as GEMM A rows whose
+    // outputs are masked by m_valid)
+    MCM_TRY(dev_alloc(h, &h->patches, (size_t)h->mp_pad * h->Kp, true));
+    MCM_TRY(dev_alloc(h, &h->x, (size_t)h->m_pad * D, true));
+    MCM_TRY(dev_alloc(h, &h->xn, (size_t)h->m_pad * D, true));
+    MCM_TRY(dev_alloc(h, &h->qkv, (size_t)h->m_pad * 3 * D, true));
+    MCM_TRY(dev_alloc(h, &h->attn, (size_t)h->m_pad * D, true));
+    MCM_TRY(dev_alloc(h, &h->hid, (size_t)h->m_pad * F, true));
+    MCM_TRY(make_tmap(h, &h->tm_patches, h->patches, h->mp_pad, h->Kp, kGemmBlockM));
+    MCM_TRY(make_tmap(h, &h->tm_xn, h->xn, h->m_pad, D, kGemmBlockM));
+    MCM_TRY(make_tmap(h, &h->tm_attn, h->attn, h->m_pad, D, kGemmBlockM));
+    MCM_TRY(make_tmap(h, &h->tm_hid, h->hid, h->m_pad, F, kGemmBlockM));
+#undef MCM_TRY
+    *out = h;
+    return MCM_OK;
+}
+
+void mcm_destroy(McmHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(h->wpatch); fr(h->cls); fr(h->pos); fr(h->pre_g); fr(h->pre_b); fr(h->post_g); fr(h->post_b); fr(h->wproj);
+    for (auto& w : h->layers) {
+        fr(w.wqkv); fr(w.wo); fr(w.w1); fr(w.w2); fr(w.bqkv); fr(w.bo); fr(w.b1); fr(w.b2);
+        fr(w.ln1g); fr(w.ln1b); fr(w.ln2g); fr(w.ln2b);
+    }
+    fr(h->stage); fr(h->bank); fr(h->patches); fr(h->x); fr(h->xn); fr(h->qkv); fr(h->attn); fr(h->hid);
+    fr(h->img_buf[0]); fr(h->img_buf[1]); fr(h->scores_buf);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : h->prof_pool) cudaEventDestroy(e);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    delete h;
+}
+
+int mcm_load_weight(McmHandle* h, const char* key, const float* data, int64_t numel, int32_t* used) {
+    if (used) *used = 0;
+    if (!h || !key || !data) return fail(h, MCM_EINVAL, "mcm_load_weight: NULL argument");
+    Dest d;
+    if (!resolve_key(h, key, &d)) return MCM_OK;  // not part of the vision path
+    const int64_t want = d.rows * d.cols;
+    if (numel != want) return fail(h, MCM_EINVAL, "%s: expected %lld elements, got %lld", key, (long long)want, (long long)numel);
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (d.f32) {
+        MCM_CUDA(h, cudaMemcpy(d.f32, data, want * sizeof(float), cudaMemcpyDefault));
+    } else {
+        MCM_CUDA(h, cudaMemcpy(h->stage, data, want * sizeof(float), cudaMemcpyDefault));
+        convert_rows_bf16_kernel<<<1024, 256>>>(h->stage, d.bf16, d.rows, d.cols, d.dst_ld);
+        MCM_CUDA(h, cudaGetLastError());
+        MCM_CUDA(h, cudaDeviceSynchronize());
+    }
+    h->loaded[d.slot] = 1;
+    h->finalized = false;
+    if (used) *used = 1;
+    return MCM_OK;
+}
+
+int mcm_finalize_weights(McmHandle* h) {
+    if (!h) return MCM_EINVAL;
+    static const char* globals[SLOT_GLOBALS] = {"vision_model.embeddings.class_embedding",
+                                                "vision_model.embeddings.patch_embedding.weight",
+                                                "vision_model.embeddings.position_embedding.weight",
+                                                "vision_model.pre_layrnorm.weight", "vision_model.pre_layrnorm.bias",
+                                                "vision_model.post_layernorm.weight", "vision_model.post_layernorm.bias",
+                                                "visual_projection.weight"};
+    for (size_t i = 0; i < h->loaded.size(); ++i) {
+        if (h->loaded[i]) continue;
+        if (i < SLOT_GLOBALS) return fail(h, MCM_ESTATE, "weight %s was never loaded", globals[i]);
+        const int li = (int)(i - SLOT_GLOBALS) / 16, which = (int)(i - SLOT_GLOBALS) % 16;
+        return fail(h, MCM_ESTATE, "weight vision_model.encoder.layers.%d.%s was never loaded", li, kLayerNames[which]);
+    }
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    MCM_CUDA(h, cudaDeviceSynchronize());
+    h->finalized = true;
+    return MCM_OK;
+}
+
+int mcm_set_text_bank(McmHandle* h, const float* bank, int32_t K, int32_t already_unit) {
+    if (!h || !bank) return fail(h, MCM_EINVAL, "mcm_set_text_bank: NULL argument");
+    if (K <= 0) return fail(h, MCM_EINVAL, "K must be positive (got %d)", K);
+    const size_t smem = sizeof(float) * (static_cast<size_t>(kTailImgs) * (h->D + h->P + K) + 8 + kTailImgs);
+    if (smem > 220 * 1024) return fail(h, MCM_EUNSUPPORTED, "prompt bank with K=%d rows does not fit the tail kernel", K);
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    MCM_CUDA(h, cudaDeviceSynchronize());
+    if (h->bank) { cudaFree(h->bank); h->bank = nullptr; h->K = 0; }
+    int rc = dev_alloc(h, &h->bank, (size_t)K * h->P, false);
+    if (rc) return rc;
+    MCM_CUDA(h, cudaMemcpy(h->bank, bank, (size_t)K * h->P * sizeof(float), cudaMemcpyDefault));
+    if (!already_unit) {
+        normalize_rows_kernel<<<(K + 7) / 8, 256>>>(h->bank, K, h->P);
+        MCM_CUDA(h, cudaGetLastError());
+    }
+    MCM_CUDA(h, cudaDeviceSynchronize());
+    h->K = K;
+    return MCM_OK;
+}
+
+int mcm_image_features(McmHandle* h, const float* images, int32_t b, float* feats, void* stream) {
+    int rc = check_ready(h, b, false);
+    if (rc) return rc;
+    if (b == 0) return MCM_OK;
+    if (!images || !feats) return fail(h, MCM_EINVAL, "mcm_image_features: NULL buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = forward_tower(h, images, b, st))) return rc;
+    return launch_tail(h, h->x, b, 1.0f, SCORE_MCM, feats, nullptr, st);
+}
+
+int mcm_score(McmHandle* h, const float* images, int32_t b, float T, int32_t kind, float* scores, void* stream) {
+    int rc = check_ready(h, b, true);
+    if (rc) return rc;
+    if (b == 0) return MCM_OK;
+    if (!images || !scores) return fail(h, MCM_EINVAL, "mcm_score: NULL buffer");
+    if (!(T > 0.f)) return fail(h, MCM_EINVAL, "temperature must be positive (got %g)", (double)T);
+    if (kind < MCM_SCORE_MCM || kind > MCM_SCORE_VAR) return fail(h, MCM_EINVAL, "unknown score kind %d", kind);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = forward_tower(h, images, b, st))) return rc;
+    return launch_tail(h, h->x, b, T, kind, nullptr, scores, st);
+}
+
+int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int32_t batch, float T, int32_t kind,
+                          float* scores_host) {
+    int rc = check_ready(h, batch, true);
+    if (rc) return rc;
+    if (n == 0) return MCM_OK;
+    if (n < 0 || batch <= 0) return fail(h, MCM_EINVAL, "n must be >= 0 and batch positive");
+    if (!images_host || !scores_host) return fail(h, MCM_EINVAL, "mcm_score_stream_host: NULL buffer");
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t img_elems = (size_t)3 * h->cfg.image_size * h->cfg.image_size;
+    if (!h->s_copy) {
+        MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MCM_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            MCM_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            if ((rc = dev_alloc(h, &h->img_buf[i], (size_t)h->cfg.max_batch * img_elems, false))) return rc;
+        }
+    }
+    if (n > h->scores_cap) {
+        if (h->scores_buf) cudaFree(h->scores_buf);
+        h->scores_buf = nullptr;
+        h->scores_cap = 0;
+        if ((rc = dev_alloc(h, &h->scores_buf, (size_t)n, false))) return rc;
+        h->scores_cap = n;
+    }
+    int64_t done = 0;
+    int it = 0;
+    while (done < n) {
+        const int cur = static_cast<int>(std::min<int64_t>(batch, n - done));
+        const int slot = it & 1;
+        if (it >= 2) MCM_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_done[slot], 0));
+        MCM_CUDA(h, cudaMemcpyAsync(h->img_buf[slot], images_host + (size_t)done * img_elems, (size_t)cur * img_elems * sizeof(float),
+                                    cudaMemcpyHostToDevice, h->s_copy));
+        MCM_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_copy));
+        MCM_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
+        if ((rc = mcm_score(h, h->img_buf[slot], cur, T, kind, h->scores_buf + done, h->s_comp))) return rc;
+        MCM_CUDA(h, cudaEventRecord(h->ev_done[slot], h->s_comp));
+        done += cur;
+        ++it;
+    }
+    MCM_CUDA(h, cudaMemcpyAsync(scores_host, h->scores_buf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->s_comp));
+    MCM_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    return MCM_OK;
+}
+
+int64_t mcm_launch_count(const McmHandle* h) { return h ? h->launches : 0; }
+void mcm_reset_launch_count(McmHandle* h) { if (h) h->launches = 0; }
+
+int mcm_profile_enable(McmHandle* h, int32_t on) {
+    if (!h) return MCM_EINVAL;
+    h->prof_on = on != 0;
+    return MCM_OK;
+}
+
+int mcm_profile_read(McmHandle* h, double* ms, int64_t* counts, int32_t reset) {
+    if (!h) return MCM_EINVAL;
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    MCM_CUDA(h, cudaDeviceSynchronize());
+    for (auto& r : h->prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.kind >= 0 && r.kind < MCM_PROF_KINDS) {
+            h->prof_ms[r.kind] += t;
+            h->prof_n[r.kind] += 1;
+        }
+        h->prof_pool.push_back(r.a);
+        h->prof_pool.push_back(r.b);
+    }
+    h->prof_recs.clear();
+    for (int i = 0; i < MCM_PROF_KINDS; ++i) {
+        if (ms) ms[i] = h->prof_ms[i];
+        if (counts) counts[i] = h->prof_n[i];
+        if (reset) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    }
+    return MCM_OK;
+}
+
+// ------------------------------------------------------------------ per-kernel entry points ----
+int mcm_dbg_gemm(McmHandle* h, const void* a, const void* w, const float* bias, const float* resid, void* out, int32_t M,
+                 int32_t N, int32_t K, int32_t epi, void* stream) {
+    if (!h || !a || !w || !out) return fail(h, MCM_EINVAL, "mcm_dbg_gemm: NULL argument");
+    if (epi < 0 || epi > 2) return fail(h, MCM_EINVAL, "mcm_dbg_gemm: epi must be 0, 1 or 2");
+    if (M <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_gemm: M must be positive");
+    if (epi == 2 && !resid) return fail(h, MCM_EINVAL, "mcm_dbg_gemm: epi 2 needs resid");
+    if (N % 128 != 0 || K % 64 != 0) return fail(h, MCM_EUNSUPPORTED, "mcm_dbg_gemm: N %% 128 and K %% 64 must be 0");
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N)))) return rc;
+    return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, epi, bias, out, resid, nullptr, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float* b, void* out, int32_t M, int32_t D,
+                      float eps, int32_t out_bf16, void* stream) {
+    if (!h || !x || !g || !b || !out) return fail(h, MCM_EINVAL, "mcm_dbg_layernorm: NULL argument");
+    return launch_layernorm(h, x, g, b, out, M, D, eps, out_bf16 != 0, static_cast<cudaStream_t>(stream));
+}
+
+int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t S, int32_t H, void* stream) {
+    if (!h || !qkv || !o) return fail(h, MCM_EINVAL, "mcm_dbg_attention: NULL argument");
+    return launch_attention(h, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(o), b, S, H,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int mcm_dbg_tail(McmHandle* h, const float* x, int32_t b, float T, int32_t kind, float* feats, float* scores, void* stream) {
+    int rc = check_ready(h, b, scores != nullptr);
+    if (rc) return rc;
+    if (!x) return fail(h, MCM_EINVAL, "mcm_dbg_tail: NULL argument");
+    return launch_tail(h, x, b, T, kind, feats, scores, static_cast<cudaStream_t>(stream));
+}
+
+int mcm_dbg_embed(McmHandle* h, const float* images, int32_t b, float* x, void* stream) {
+    int rc = check_ready(h, b, false);
+    if (rc) return rc;
+    if (!images || !x) return fail(h, MCM_EINVAL, "mcm_dbg_embed: NULL argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // run only pre_layrnorm here: the fused LN1 output goes to the workspace, x is copied out
+    if ((rc = launch_embed(h, images, b, st))) return rc;
+    MCM_CUDA(h, cudaMemcpyAsync(x, h->x, (size_t)b * h->S * h->D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return MCM_OK;
+}
+
+}  // extern "C"

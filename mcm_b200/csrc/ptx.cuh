@@ -8,10 +8,11 @@
 
 namespace mcm {
 
-#ifndef MCM_SPIN_LIMIT
-// mbarrier waits trap instead of hanging the GPU if a pipeline deadlocks
-// (about a second of spinning); set to 0 to compile the guard out.
-#define MCM_SPIN_LIMIT (1u << 26)
+#ifndef MCM_WAIT_TIMEOUT_CYCLES
+// mbarrier waits trap instead of hanging the GPU if a pipeline deadlocks (about two seconds of
+// SM clocks; every legitimate wait in this library is far below a millisecond).  0 compiles the
+// guard out.
+#define MCM_WAIT_TIMEOUT_CYCLES 4000000000ll
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -64,11 +65,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if MCM_SPIN_LIMIT
-    uint32_t spins = 0;
+#if MCM_WAIT_TIMEOUT_CYCLES
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > MCM_SPIN_LIMIT) {
-            printf("mcm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+        if (clock64() - t0 > MCM_WAIT_TIMEOUT_CYCLES) {
+            printf("mcm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
                    smem_u32(bar), parity);
             __trap();
         }

@@ -1,0 +1,162 @@
+// HBM-bound row-wise kernels of the vision tower: patch gather, LayerNorm, embedding finish.
+// One warp owns one token row; rows live in registers as float4 (lane-strided, fully coalesced
+// 512-byte warp transactions); all statistics are fp32 with warp-shuffle reductions.
+//
+// Reference arithmetic: nn.LayerNorm (biased variance, eps inside the sqrt) as used by HF CLIP,
+//   pre_layrnorm HF:modeling_clip.py:659,677; layer_norm1/2 HF:359-361,371,380;
+//   embeddings (CLS concat + position add) HF:212-217.
+#pragma once
+#include "ptx.cuh"
+
+namespace mcm {
+
+constexpr int kRowThreads = 256;  // 8 warps = 8 rows per CTA
+
+// Row of D = 128 * VEC floats held by a warp: element (v, lane, c) <-> column (v * 32 + lane) * 4 + c.
+template <int VEC>
+struct WarpRow {
+    float4 v[VEC];
+
+    __device__ __forceinline__ void load(const float* __restrict__ src, int lane) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = s4[i * 32 + lane];
+    }
+    __device__ __forceinline__ void load_ro(const float* __restrict__ src, int lane) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = __ldg(s4 + i * 32 + lane);
+    }
+    __device__ __forceinline__ void add_ro(const float* __restrict__ src, int lane) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float4 a = __ldg(s4 + i * 32 + lane);
+            v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+        }
+    }
+    // (x - mean) * rstd * gamma + beta, in place
+    __device__ __forceinline__ void layernorm(const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                              int lane) {
+        constexpr float inv_d = 1.0f / (128.0f * VEC);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float mean = warp_sum(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+        const float4* g4 = reinterpret_cast<const float4*>(gamma);
+        const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float4 g = __ldg(g4 + i * 32 + lane);
+            const float4 b = __ldg(b4 + i * 32 + lane);
+            v[i].x = (v[i].x - mean) * rstd * g.x + b.x;
+            v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
+            v[i].z = (v[i].z - mean) * rstd * g.z + b.z;
+            v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
+        }
+    }
+    __device__ __forceinline__ void store_f32(float* __restrict__ dst, int lane) const {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d4[i * 32 + lane] = v[i];
+    }
+    __device__ __forceinline__ void store_bf16(__nv_bfloat16* __restrict__ dst, int lane) const {
+        uint2* d2 = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d2[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+    }
+};
+
+// x f32 [M, D] -> LayerNorm -> bf16 or f32 [M, D]
+template <int VEC, bool OUT_BF16>
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 void* __restrict__ out, int M, float eps) {
+    constexpr int D = 128 * VEC;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    WarpRow<VEC> r;
+    r.load(x + static_cast<size_t>(row) * D, lane);
+    r.layernorm(gamma, beta, eps, lane);
+    if constexpr (OUT_BF16)
+        r.store_bf16(static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(row) * D, lane);
+    else
+        r.store_f32(static_cast<float*>(out) + static_cast<size_t>(row) * D, lane);
+}
+
+// Finish the embeddings after the patch GEMM has written  patch . W + pos  into the patch rows of x:
+//   row b*S      <- class_embedding + pos[0]                    (HF:212-213,217)
+//   every row    <- pre_layrnorm(row)                            (HF:677)   -> x   (fp32 residual stream)
+//   and          <- layer_norm1 of layer 0 applied on top        (HF:371)   -> xn  (bf16 GEMM operand)
+template <int VEC>
+__global__ void __launch_bounds__(kRowThreads)
+embed_finish_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xn, const float* __restrict__ cls,
+                    const float* __restrict__ pos, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
+                    const float* __restrict__ ln1_g, const float* __restrict__ ln1_b, int M, int S, float eps) {
+    constexpr int D = 128 * VEC;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    WarpRow<VEC> r;
+    if (row % S == 0) {
+        r.load_ro(cls, lane);
+        r.add_ro(pos, lane);
+    } else {
+        r.load(x + static_cast<size_t>(row) * D, lane);
+    }
+    r.layernorm(pre_g, pre_b, eps, lane);
+    r.store_f32(x + static_cast<size_t>(row) * D, lane);
+    if (xn != nullptr) {
+        r.layernorm(ln1_g, ln1_b, eps, lane);
+        r.store_bf16(xn + static_cast<size_t>(row) * D, lane);
+    }
+}
+
+// Patch gather ("im2col" of the stride = kernel = patch conv, HF:148-154,209-210):
+//   images f32 [b, 3, H, W] NCHW  ->  patches bf16 [b * G * G, Kp],  column = c * p * p + i * p + j
+// (the flattening order of the conv weight [D, 3, p, p]); columns >= 3 p^2 (K padding) are never
+// written and stay zero.  One CTA copies the 3 * p image rows that make up one row of G patches:
+// reads are contiguous 224-float image rows, writes are p-element runs.
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches, int G, int p, int Kp) {
+    const int W = G * p;
+    const int gy = blockIdx.x % G;
+    const int b = blockIdx.x / G;
+    const int half_w = W >> 1;
+    const int n = 3 * p * half_w;  // float2 items in this patch row
+    const float* src_img = img + static_cast<size_t>(b) * 3 * W * W;
+    __nv_bfloat16* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int xh = t % half_w;
+        const int ci = t / half_w;  // c * p + i
+        const int i = ci % p;
+        const int c = ci / p;
+        const int x = xh * 2;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src_img + (static_cast<size_t>(c) * W + gy * p + i) * W + x));
+        const int gx = x / p;
+        const int j = x - gx * p;
+        *reinterpret_cast<uint32_t*>(dst_row + static_cast<size_t>(gx) * Kp + (c * p + i) * p + j) = pack_bf16x2(v.x, v.y);
+    }
+}
+
+// fp32 -> bf16 with row re-striding (weight packing): dst[r * dst_ld + c] = src[r * cols + c]
+__global__ void convert_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
+                                         int cols, int dst_ld) {
+    const int64_t total = rows * cols;
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = t / cols;
+        const int c = static_cast<int>(t - r * cols);
+        dst[r * dst_ld + c] = __float2bfloat16_rn(src[t]);
+    }
+}
+
+}  // namespace mcm

@@ -1,0 +1,274 @@
+"""Host side of the B200 MCM engine: a thin PyTorch-facing wrapper over the C ABI.
+
+PyTorch is plumbing here (device buffers, streams); every FLOP of the path runs in the
+hand-written sm_100a kernels behind ``include/mcm_b200.h``.
+
+Two seams of the reference are re-created on top of :class:`McmEngine`:
+
+* seam 2, the model object returned by ``set_model_clip`` (``utils/train_eval_util.py:15-36``):
+  :class:`B200ClipNet` -- ``.eval()``, ``.get_image_features(pixel_values=)``,
+  ``.get_text_features(input_ids=, attention_mask=)``;
+* seam 1, ``get_ood_scores_clip`` (``utils/detection_util.py:209-249``): in
+  ``mcm_b200/detection_util.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import CFGS, CKPT_TO_CFG, VisionCfg
+
+__all__ = ["McmEngine", "B200ClipNet", "VisionCfg", "CFGS"]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _score_kind(score: str) -> int:
+    try:
+        return _lib.SCORE_KINDS[score]
+    except KeyError:
+        raise ValueError(f"score {score!r} is not part of the B200 path (choices: {sorted(_lib.SCORE_KINDS)}); "
+                         "'maha' is a different method (utils/detection_util.py:148-207)") from None
+
+
+class McmEngine:
+    """One CLIP vision tower + prompt bank resident on one B200.
+
+    Replaces, for the MCM path, ``CLIPModel.from_pretrained(...).cuda()``
+    (``utils/train_eval_util.py:23-26``) and the arithmetic of
+    ``utils/detection_util.py:225-248``.
+    """
+
+    def __init__(self, cfg: VisionCfg, max_batch: int = 256, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mcm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._lib = _lib.load()
+        self.cfg = cfg
+        self.max_batch = int(max_batch)
+        self.device = torch.device("cuda", int(device))
+        self._ccfg = _lib.McmConfig(cfg.image_size, cfg.patch, cfg.width, cfg.layers, cfg.heads, cfg.mlp, cfg.proj,
+                                    cfg.eps, self.max_batch, int(device))
+        self._h = C.c_void_p()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            _lib.check(self._lib.mcm_create(C.byref(self._ccfg), C.byref(self._h)), None)
+        self.K = 0
+
+    # ------------------------------------------------------------------ lifecycle --
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mcm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.check(rc, self._h)
+
+    # -------------------------------------------------------------------- weights --
+    def load_state_dict(self, sd: Mapping[str, torch.Tensor]) -> list:
+        """Feed a HuggingFace ``CLIPModel.state_dict()`` (fp32).  Returns the keys consumed; text
+        tower / logit_scale entries are ignored.  Raises if a vision tensor is missing."""
+        used_keys = []
+        used = C.c_int32(0)
+        for k, v in sd.items():
+            if not (k.startswith("vision_model.") or k == "visual_projection.weight"):
+                continue
+            if not torch.is_tensor(v) or not v.dtype.is_floating_point:
+                continue
+            t = v.detach().to(torch.float32).contiguous()
+            self._check(self._lib.mcm_load_weight(self._h, k.encode(), _ptr(t), t.numel(), C.byref(used)))
+            if used.value:
+                used_keys.append(k)
+        self._check(self._lib.mcm_finalize_weights(self._h))
+        return used_keys
+
+    @classmethod
+    def from_state_dict(cls, sd, cfg: VisionCfg, max_batch: int = 256, device: int = 0) -> "McmEngine":
+        e = cls(cfg, max_batch, device)
+        e.load_state_dict(sd)
+        return e
+
+    def set_text_bank(self, bank, already_unit: bool = False) -> None:
+        """Install the pre-encoded prompt bank ``[K, P]`` (rows are L2-normalised on the device like
+        ``utils/detection_util.py:231`` unless ``already_unit``)."""
+        t = torch.as_tensor(bank).detach().to(torch.float32).contiguous()
+        if t.dim() != 2 or t.shape[1] != self.cfg.proj:
+            raise ValueError(f"text bank must be [K, {self.cfg.proj}], got {tuple(t.shape)}")
+        self._check(self._lib.mcm_set_text_bank(self._h, _ptr(t), t.shape[0], 1 if already_unit else 0))
+        self.K = int(t.shape[0])
+
+    # -------------------------------------------------------------------- compute --
+    def _check_images(self, images: torch.Tensor) -> int:
+        c = self.cfg
+        if not torch.is_tensor(images) or images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError("pixel_values must be a [b, 3, H, W] tensor")
+        if images.shape[2] != c.image_size or images.shape[3] != c.image_size:
+            # same condition and wording as HF CLIPVisionEmbeddings.forward (HF:204-207)
+            raise ValueError(f"Input image size ({images.shape[2]}*{images.shape[3]}) doesn't match model "
+                             f"({c.image_size}*{c.image_size}).")
+        if images.device != self.device:
+            raise ValueError(f"pixel_values must live on {self.device}, got {images.device}")
+        if images.dtype != torch.float32:
+            raise ValueError(f"pixel_values must be float32 (the reference preprocess yields fp32), got {images.dtype}")
+        if images.shape[0] > self.max_batch:
+            raise ValueError(f"batch {images.shape[0]} exceeds max_batch {self.max_batch}")
+        return int(images.shape[0])
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def image_features(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """``net.get_image_features(pixel_values=...)`` -> un-normalised ``[b, P]`` fp32 features."""
+        b = self._check_images(pixel_values)
+        x = pixel_values.contiguous()
+        out = torch.empty((b, self.cfg.proj), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_image_features(self._h, _ptr(x), b, _ptr(out), self._stream()))
+        return out
+
+    def score(self, images: torch.Tensor, T: float = 1.0, score: str = "MCM",
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One batch of ``utils/detection_util.py:225-248``: device tensor ``[b]`` of scores
+        (asynchronous on the current stream)."""
+        b = self._check_images(images)
+        x = images.contiguous()
+        if out is None:
+            out = torch.empty((b,), dtype=torch.float32, device=self.device)
+        elif out.numel() < b or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 device tensor with at least b elements")
+        self._check(self._lib.mcm_score(self._h, _ptr(x), b, float(T), _score_kind(score), _ptr(out), self._stream()))
+        return out[:b]
+
+    def score_stream_host(self, images_host, batch: Optional[int] = None, T: float = 1.0,
+                          score: str = "MCM") -> np.ndarray:
+        """Whole evaluation stream from HOST memory (the loop of ``utils/detection_util.py:220-249``):
+        H2D copies overlap the scoring of the previous batch; returns float32 numpy ``[n]``."""
+        t = torch.as_tensor(images_host)
+        if t.device.type != "cpu" or t.dtype != torch.float32:
+            raise ValueError("images_host must be a float32 CPU tensor / ndarray")
+        t = t.contiguous()
+        c = self.cfg
+        if t.dim() != 4 or tuple(t.shape[1:]) != (3, c.image_size, c.image_size):
+            raise ValueError(f"images_host must be [n, 3, {c.image_size}, {c.image_size}], got {tuple(t.shape)}")
+        n = int(t.shape[0])
+        batch = int(batch or self.max_batch)
+        out = np.empty((n,), dtype=np.float32)
+        if n:
+            self._check(self._lib.mcm_score_stream_host(self._h, _ptr(t), n, batch, float(T), _score_kind(score),
+                                                        C.c_void_p(out.ctypes.data)))
+        return out
+
+    # ------------------------------------------------- per-kernel entry points (tests, bench) --
+    def dbg_gemm(self, a, w, bias, resid=None, epi: int = 0):
+        """epilogue(A[M,K] @ W[N,K]^T) through the tcgen05 GEMM; a, w bf16.  epi 0/1 -> bf16, 2 -> fp32."""
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32 if epi == 2 else torch.bfloat16, device=self.device)
+        self._check(self._lib.mcm_dbg_gemm(self._h, _ptr(a.contiguous()), _ptr(w.contiguous()), _ptr(bias),
+                                           _ptr(resid), _ptr(out), M, N, K, int(epi), self._stream()))
+        return out
+
+    def dbg_layernorm(self, x, gamma, beta, eps: float = 1e-5, out_bf16: bool = True):
+        M, D = x.shape
+        out = torch.empty((M, D), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=self.device)
+        self._check(self._lib.mcm_dbg_layernorm(self._h, _ptr(x.contiguous()), _ptr(gamma), _ptr(beta), _ptr(out), M, D,
+                                                float(eps), 1 if out_bf16 else 0, self._stream()))
+        return out
+
+    def dbg_attention(self, qkv, b: int, S: int, H: int):
+        out = torch.empty((b * S, H * 64), dtype=torch.bfloat16, device=self.device)
+        self._check(self._lib.mcm_dbg_attention(self._h, _ptr(qkv.contiguous()), _ptr(out), b, S, H, self._stream()))
+        return out
+
+    def dbg_tail(self, x, b: int, T: float = 1.0, score: str = "MCM", want_feats=True, want_scores=True):
+        feats = torch.empty((b, self.cfg.proj), dtype=torch.float32, device=self.device) if want_feats else None
+        scores = torch.empty((b,), dtype=torch.float32, device=self.device) if want_scores else None
+        self._check(self._lib.mcm_dbg_tail(self._h, _ptr(x.contiguous()), b, float(T), _score_kind(score), _ptr(feats),
+                                           _ptr(scores), self._stream()))
+        return feats, scores
+
+    def dbg_embed(self, images):
+        b = self._check_images(images)
+        x = torch.empty((b * self.cfg.seq, self.cfg.width), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_dbg_embed(self._h, _ptr(images.contiguous()), b, _ptr(x), self._stream()))
+        return x
+
+    # ---------------------------------------------------------------- bookkeeping --
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mcm_launch_count(self._h))
+
+    def reset_launch_count(self) -> None:
+        self._lib.mcm_reset_launch_count(self._h)
+
+    def profile(self, on: bool) -> None:
+        """Bracket every launch with CUDA events (bench.py's per-kernel roofline)."""
+        self._check(self._lib.mcm_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kind: (total_ms, launches)} accumulated since the last reset (synchronises)."""
+        n = len(_lib.PROF_KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self._lib.mcm_profile_read(self._h, ms, cnt, 1 if reset else 0))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROF_KINDS)}
+
+    def flops_per_image(self, K: Optional[int] = None) -> float:
+        return float(self._lib.mcm_flops_per_image(C.byref(self._ccfg), int(self.K if K is None else K)))
+
+
+class B200ClipNet:
+    """Duck-typed stand-in for the ``net`` the reference threads through its functions
+    (``eval_ood_detection.py:60-61``): image side on the B200 engine, text side (run once per label
+    set, not a kernel target -- SURVEY.md section 2.1 row 4) delegated to ``text_model`` (any object
+    with HF's ``get_text_features``) or replaced by a pre-encoded ``text_bank``."""
+
+    def __init__(self, engine: McmEngine, text_model=None, text_bank=None):
+        self.engine = engine
+        self.text_model = text_model
+        self.text_bank = None if text_bank is None else torch.as_tensor(text_bank, dtype=torch.float32)
+
+    def eval(self):
+        if self.text_model is not None and hasattr(self.text_model, "eval"):
+            self.text_model.eval()
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def get_image_features(self, pixel_values=None, **kw):
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")
+        return self.engine.image_features(pixel_values)
+
+    @torch.no_grad()
+    def get_text_features(self, input_ids=None, attention_mask=None, **kw):
+        if self.text_bank is not None:
+            return self.text_bank.clone()
+        if self.text_model is None:
+            raise RuntimeError("B200ClipNet has neither a text_model nor a pre-encoded text_bank")
+        dev = next(self.text_model.parameters()).device
+        out = self.text_model.get_text_features(input_ids=input_ids.to(dev),
+                                                attention_mask=None if attention_mask is None else attention_mask.to(dev),
+                                                **kw)
+        # transformers >= 5 returns BaseModelOutputWithPooling, 4.x the projected tensor
+        return out.pooler_output if hasattr(out, "pooler_output") else out
+
+
+def engine_for_ckpt(ckpt: str, state_dict, max_batch: int = 256, device: int = 0) -> McmEngine:
+    """``--CLIP_ckpt`` / ``args.ckpt`` -> engine (mapping of ``utils/train_eval_util.py:19-22``)."""
+    names = {"ViT-B/32": "ViT-B/32", "ViT-B/16": "ViT-B/16", "ViT-L/14": "ViT-L/14", **CKPT_TO_CFG}
+    if ckpt not in names:
+        raise ValueError(f"unknown CLIP checkpoint {ckpt!r}")
+    return McmEngine.from_state_dict(state_dict, CFGS[names[ckpt]], max_batch=max_batch, device=device)

@@ -1,0 +1,133 @@
+"""Drop-in boundary behaviour: reference signature / return contract / error behaviour
+(utils/detection_util.py:209-249; HF modeling_clip.py:204-207), ragged and empty streams,
+the host-stream C-ABI entry point, launch accounting."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ListLoader, make_args
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tiny_net(engine_factory):
+    from mcm_b200 import synth
+    from mcm_b200.engine import B200ClipNet
+    eng, sd, cfg = engine_factory("tiny", 5, 32)
+    bank = synth.synth_unit_bank(12, cfg.proj, 9)
+    return B200ClipNet(eng, text_bank=bank).eval(), cfg, bank
+
+
+def test_return_contract_and_ragged_batches(tiny_net):
+    from mcm_b200 import detection_util as DU
+    from mcm_b200 import synth
+    net, cfg, bank = tiny_net
+    imgs = synth.synth_images(77, 3)
+    labels = [f"c{i}" for i in range(12)]
+    a = DU.get_ood_scores_clip(make_args(), net, ListLoader(imgs, 32), labels, in_dist=True)   # 32+32+13
+    b = DU.get_ood_scores_clip(make_args(), net, ListLoader(imgs, 7), labels)                  # 11 ragged batches
+    c = DU.get_ood_scores_clip(make_args(), net, ListLoader(imgs, 100), labels)                # loader batch > max_batch
+    assert a.dtype == np.float32 and a.shape == (77,) and a.flags["OWNDATA"]
+    np.testing.assert_array_equal(a, b)          # a score depends only on its own image: batch-invariant, bit-exact
+    np.testing.assert_array_equal(a, c)
+    assert np.all(a < 0) and np.all(a >= -1)     # -max softmax
+    e = DU.get_ood_scores_clip(make_args(), net, ListLoader(imgs[:0], 8), labels)
+    assert e.shape == (0,) and e.dtype == np.float32
+
+
+def test_scores_are_deterministic(tiny_net):
+    from mcm_b200 import synth
+    net, cfg, _ = tiny_net
+    x = torch.from_numpy(synth.synth_images(16, 4)).cuda()
+    s1 = net.engine.score(x).clone()
+    s2 = net.engine.score(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s2)
+
+
+def test_host_stream_matches_device_path(tiny_net):
+    from mcm_b200 import synth
+    net, cfg, _ = tiny_net
+    eng = net.engine
+    imgs = synth.synth_images(70, 5)
+    dev = torch.cat([eng.score(torch.from_numpy(imgs[s:s + 32]).cuda()) for s in range(0, 70, 32)]).cpu().numpy()
+    pinned = torch.from_numpy(imgs).pin_memory()
+    for batch in (32, 9):
+        host = eng.score_stream_host(pinned, batch=batch)
+        np.testing.assert_array_equal(host, dev)
+    np.testing.assert_array_equal(eng.score_stream_host(imgs, batch=16), dev)    # pageable host memory works too
+    assert eng.score_stream_host(imgs[:0]).shape == (0,)
+
+
+def test_all_score_kinds_via_args(tiny_net):
+    from mcm_b200 import detection_util as DU
+    from mcm_b200 import synth
+    from oracle import clip_mcm_oracle as O
+    net, cfg, bank = tiny_net
+    imgs = synth.synth_images(20, 6)
+    labels = [f"c{i}" for i in range(12)]
+    feats = net.get_image_features(pixel_values=torch.from_numpy(imgs).cuda()).cpu()
+    for sc in ("MCM", "max-logit", "energy", "entropy", "var"):
+        got = DU.get_ood_scores_clip(make_args(T=2, score=sc), net, ListLoader(imgs, 8), labels)
+        ref = O.scores_from_features(feats, torch.from_numpy(bank), 2, sc)
+        np.testing.assert_allclose(got, ref, rtol=3e-4, atol=3e-6, err_msg=sc)
+
+
+def test_error_behaviour(tiny_net):
+    from mcm_b200 import detection_util as DU
+    from mcm_b200 import synth
+    net, cfg, _ = tiny_net
+    eng = net.engine
+    with pytest.raises(ValueError, match="doesn't match model"):      # HF:204-207
+        eng.score(torch.zeros(2, 3, 192, 192, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.score(torch.zeros(2, 3, 224, 224))                          # host tensor on the device path
+    with pytest.raises(ValueError):
+        eng.score(torch.zeros(2, 3, 224, 224, device="cuda", dtype=torch.float16))
+    with pytest.raises(ValueError):
+        eng.score(torch.zeros(33, 3, 224, 224, device="cuda"))          # > max_batch
+    with pytest.raises(ValueError):
+        eng.score(torch.zeros(2, 3, 224, 224, device="cuda"), score="maha")
+    with pytest.raises(ValueError):
+        eng.score(torch.zeros(2, 3, 224, 224, device="cuda"), T=0)
+    with pytest.raises(ValueError):
+        eng.set_text_bank(np.zeros((4, cfg.proj + 1), np.float32))
+    with pytest.raises(TypeError):
+        DU.get_ood_scores_clip(make_args(), torch.nn.Linear(2, 2), ListLoader(synth.synth_images(1, 1), 1), ["a"])
+
+
+def test_bank_and_weights_required(engine_factory):
+    from mcm_b200 import synth
+    from mcm_b200.engine import McmEngine
+    cfg = synth.CFGS["tiny"]
+    eng = McmEngine(cfg, max_batch=4)
+    try:
+        x = torch.zeros(1, 3, 224, 224, device="cuda")
+        with pytest.raises(RuntimeError, match="not finalized"):
+            eng.score(x)
+        sd = synth.synth_vision_state_dict(cfg, 5)
+        partial = {k: v for k, v in sd.items() if "layers.1.mlp.fc2.weight" not in k}
+        with pytest.raises(RuntimeError, match="never loaded"):
+            eng.load_state_dict(partial)
+        used = eng.load_state_dict({**sd, "logit_scale": torch.tensor(1.0), "text_model.foo": torch.zeros(3)})
+        assert len(used) == len(sd)
+        with pytest.raises(RuntimeError, match="bank is not set"):
+            eng.score(x)
+        eng.image_features(x)       # needs no bank
+        bad = dict(sd)
+        bad["visual_projection.weight"] = torch.zeros(3, 3)
+        with pytest.raises(ValueError, match="expected"):
+            eng.load_state_dict(bad)
+    finally:
+        eng.close()
+
+
+def test_launch_count(tiny_net):
+    net, cfg, _ = tiny_net
+    eng = net.engine
+    eng.reset_launch_count()
+    eng.score(torch.zeros(3, 3, 224, 224, device="cuda"))
+    torch.cuda.synchronize()
+    # patchify + patch GEMM + embed_finish + L * (3 GEMM... ) : 3 + 7 L - 1 + tail
+    assert eng.launch_count == 3 + 7 * cfg.layers - 1 + 1

@@ -1,0 +1,42 @@
+"""The CPU oracle restatement against the golden vectors produced by the UNMODIFIED reference
+(utils/detection_util.py:209-249 + HF CLIP) in the authoring container -- the pin that lets the
+oracle be trusted as the checker of the CUDA path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_inputs
+from oracle import clip_mcm_oracle as O
+
+
+@pytest.mark.parametrize("case", ["tiny_text_k10", "tiny_proto_k16_T2", "small_proto_k20"])
+def test_oracle_reproduces_reference_scores(case, golden_dir):
+    z = np.load(os.path.join(golden_dir, case + ".npz"))
+    cfg, sd, _protos, id_imgs, ood_imgs = golden_inputs(z)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for sc in [str(s) for s in z["scores"]]:
+        key = sc.replace("-", "_")
+        o_in = O.ood_scores(id_imgs, sd, cfg, z["bank"], T=int(z["T"]), score=sc, batch=64)
+        o_out = O.ood_scores(ood_imgs, sd, cfg, z["bank"], T=int(z["T"]), score=sc, batch=64)
+        assert o_in.dtype == np.float32
+        scale = max(1.0, float(np.abs(z[f"ref_in_{key}"]).max()))
+        np.testing.assert_allclose(o_in, z[f"ref_in_{key}"], rtol=0, atol=4e-6 * scale)
+        np.testing.assert_allclose(o_out, z[f"ref_out_{key}"], rtol=0, atol=4e-6 * scale)
+        m = O.get_measures(-z[f"ref_in_{key}"], -z[f"ref_out_{key}"])
+        np.testing.assert_allclose(m, z[f"measures_{key}"], rtol=0, atol=1e-12)
+
+
+def test_oracle_b16_subset(golden_dir):
+    """ViT-B/16 (BASELINE config 1): 12 of the 256 ID images, to keep the CPU suite short."""
+    z = np.load(os.path.join(golden_dir, "b16_text_k10_cfg1.npz"))
+    cfg, sd, _protos, id_imgs, _ood = golden_inputs(dict(z, n_id=12, n_ood=1))
+    torch.set_num_threads(os.cpu_count() or 1)
+    o_in = O.ood_scores(id_imgs[:12], sd, cfg, z["bank"], T=1, score="MCM", batch=12)
+    np.testing.assert_allclose(o_in, z["ref_in_MCM"][:12], rtol=0, atol=4e-6)
+
+
+def test_flops_formula():
+    assert O.flops_per_image(O.CFGS["ViT-B/16"], 1000) == pytest.approx(35.128e9, rel=2e-4)
+    assert O.flops_per_image(O.CFGS["ViT-L/14"], 1000) == pytest.approx(162.027e9, rel=2e-4)
