@@ -238,6 +238,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tcgen05_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
