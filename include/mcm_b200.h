@@ -63,7 +63,7 @@ typedef struct McmConfig {
     int32_t layers;      /* num_hidden_layers L                                     */
     int32_t heads;       /* num_attention_heads H; D / H must be 64                 */
     int32_t mlp;         /* intermediate_size F; multiple of 128                    */
-    int32_t proj;        /* projection_dim P; multiple of 4                         */
+    int32_t proj;        /* projection_dim P; multiple of 16                        */
     float eps;           /* layer_norm_eps (1e-5)                                   */
     int32_t max_batch;   /* largest `b` a single mcm_score call will be given       */
     int32_t device;      /* CUDA ordinal                                            */
@@ -86,7 +86,7 @@ const char* mcm_last_error(const McmHandle* h);
 int mcm_load_weight(McmHandle* h, const char* hf_key, const float* data, int64_t numel, int32_t* used);
 
 /* Verify that every tensor of the vision path arrived and convert/pack them for the kernels
- * (bf16 GEMM operands, fused QKV weight, padded patch filter).  Must precede any compute call. */
+ * (fp16 GEMM operands, fused QKV weight, padded patch filter).  Must precede any compute call. */
 int mcm_finalize_weights(McmHandle* h);
 
 /* Install the pre-encoded prompt bank: `bank` is [K,P] fp32 (host or device), one row per entry
@@ -117,6 +117,13 @@ int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int
 int64_t mcm_launch_count(const McmHandle* h);
 void mcm_reset_launch_count(McmHandle* h);
 
+/* Engine options.  MCM_OPT_CLS_SHORTCUT (default 1): in the LAST encoder layer run attention,
+ * out_proj, layer_norm2 and the MLP only for the CLS query row of every image -- the only row the
+ * reference consumes afterwards (pooled = last_hidden_state[:, 0], HF:685).  Results are
+ * identical; 0 runs the full last layer (the number bench.py reports beside the default). */
+enum { MCM_OPT_CLS_SHORTCUT = 1 };
+int mcm_set_option(McmHandle* h, int32_t option, int32_t value);
+
 /* Optional per-launch timing for bench.py's roofline: while enabled, every kernel launch of a
  * forward is bracketed by CUDA events on the launching stream.  mcm_profile_read synchronises the
  * device and returns accumulated milliseconds and launch counts per kernel kind (arrays of
@@ -138,16 +145,16 @@ int32_t mcm_abi_version(void);
  *      reference of the same op, and by bench.py for the per-kernel roofline).  All pointers are
  *      device pointers; all calls are asynchronous on `stream`. ---- */
 
-/* out = epilogue(A[M,K] @ W[N,K]^T): A, W bf16 row-major.
- * epi 0: out bf16 = acc + bias            1: out bf16 = quick_gelu(acc + bias)
+/* out = epilogue(A[M,K] @ W[N,K]^T): A, W fp16 row-major.
+ * epi 0: out fp16 = acc + bias            1: out fp16 = quick_gelu(acc + bias)
  * epi 2: out f32  = resid + acc + bias    (resid may alias out) */
-int mcm_dbg_gemm(McmHandle* h, const void* a_bf16, const void* w_bf16, const float* bias, const float* resid,
+int mcm_dbg_gemm(McmHandle* h, const void* a_f16, const void* w_f16, const float* bias, const float* resid,
                  void* out, int32_t M, int32_t N, int32_t K, int32_t epi, void* stream);
-/* nn.LayerNorm over the last dim (HF:359-361): x f32 [M,D] -> out bf16 (out_bf16 != 0) or f32. */
+/* nn.LayerNorm over the last dim (HF:359-361): x f32 [M,D] -> out fp16 (out_f16 != 0) or f32. */
 int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* gamma, const float* beta, void* out, int32_t M,
-                      int32_t D, float eps, int32_t out_bf16, void* stream);
-/* softmax(q k^T / 8) v per (image, head) (HF:261-279,318-331): qkv bf16 [b*S, 3*H*64] -> o bf16 [b*S, H*64]. */
-int mcm_dbg_attention(McmHandle* h, const void* qkv_bf16, void* o_bf16, int32_t b, int32_t S, int32_t H,
+                      int32_t D, float eps, int32_t out_f16, void* stream);
+/* softmax(q k^T / 8) v per (image, head) (HF:261-279,318-331): qkv fp16 [b*S, 3*H*64] -> o fp16 [b*S, H*64]. */
+int mcm_dbg_attention(McmHandle* h, const void* qkv_f16, void* o_f16, int32_t b, int32_t S, int32_t H,
                       void* stream);
 /* CLS pool + post_layernorm + visual_projection (HF:685-686,860-861) + the scoring tail.
  * x f32 [b*S, D] (row b*S is the CLS token); feats (may be NULL) [b,P]; scores (may be NULL) [b]. */

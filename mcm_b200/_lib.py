@@ -17,6 +17,8 @@ OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = range(6)
 PROF_KINDS = ["patchify", "gemm_patch", "embed_finish", "gemm_qkv", "attention", "gemm_out", "layernorm",
               "gemm_fc1", "gemm_fc2", "tail", "gemm_other"]
 
+OPT_CLS_SHORTCUT = 1
+
 SCORE_KINDS = {"MCM": 0, "max-logit": 1, "energy": 2, "entropy": 3, "var": 4}
 
 
@@ -44,6 +46,7 @@ SIGNATURES = {
     "mcm_score_stream_host": (C.c_int, [_H, _P, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
     "mcm_launch_count": (C.c_int64, [_H]),
     "mcm_reset_launch_count": (None, [_H]),
+    "mcm_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "mcm_profile_enable": (C.c_int, [_H, C.c_int32]),
     "mcm_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "mcm_flops_per_image": (C.c_double, [C.POINTER(McmConfig), C.c_int32]),

@@ -2,43 +2,43 @@
 // non-causal, no mask (HF:modeling_clip.py:261-279 eager == what SDPA computes, :318-331).
 //
 // 4 % of the tower's FLOPs.  This version keeps the whole K and V of one head in
-// shared memory (S <= 272 keys x 64 x bf16 = 34 KB each), gives every warp 16-query-row tiles, and
+// shared memory (S <= 272 keys x 64 x fp16 = 34 KB each), gives every warp 16-query-row tiles, and
 // runs flash-style online softmax over 64-key chunks with warp-level mma.sync tiles
-// (m16n8k16 bf16 -> fp32).  Scores, running max / sum and the output accumulator stay in fp32
-// registers; probabilities are rounded to bf16 only as the A operand of P.V.
+// (m16n8k16 fp16 -> fp32).  Scores, running max / sum and the output accumulator stay in fp32
+// registers; probabilities are rounded to fp16 only as the A operand of P.V.
 //
-// qkv: bf16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)
-// out: bf16 [b * S, H * 64]      (== attn_output.transpose(1,2).reshape(B,S,D), HF:333)
+// qkv: fp16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)
+// out: fp16 [b * S, H * 64]      (== attn_output.transpose(1,2).reshape(B,S,D), HF:333)
 #pragma once
 #include "ptx.cuh"
 
 namespace mcm {
 
 constexpr int kAttnDh = 64;
-constexpr int kAttnLd = 72;      // smem row stride in bf16 (144 B): ldmatrix rows fall in distinct banks
+constexpr int kAttnLd = 72;      // smem row stride in fp16 (144 B): ldmatrix rows fall in distinct banks
 constexpr int kAttnChunk = 64;   // keys per online-softmax step
 
 __global__ void __launch_bounds__(288)
-attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int H,
+attention_mma_kernel(const op16_t* __restrict__ qkv, op16_t* __restrict__ out, int S, int H,
                      int keys_pad /* S rounded up to 16 */, float scale_log2e) {
     extern __shared__ __align__(16) uint8_t attn_smem[];
-    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(attn_smem);
-    __nv_bfloat16* sV = sK + static_cast<size_t>(keys_pad) * kAttnLd;
+    op16_t* sK = reinterpret_cast<op16_t*>(attn_smem);
+    op16_t* sV = sK + static_cast<size_t>(keys_pad) * kAttnLd;
 
     const int h = blockIdx.x % H;
     const int img = blockIdx.x / H;
     const int ld = 3 * H * kAttnDh;
-    const __nv_bfloat16* base = qkv + static_cast<size_t>(img) * S * ld + h * kAttnDh;
+    const op16_t* base = qkv + static_cast<size_t>(img) * S * ld + h * kAttnDh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
 
     // ---- stage K and V of this head (zero rows beyond S) ----
     for (int t = threadIdx.x; t < keys_pad * 8; t += blockDim.x) {
         const int r = t >> 3, c = (t & 7) * 8;
-        __nv_bfloat16* dk = sK + r * kAttnLd + c;
-        __nv_bfloat16* dv = sV + r * kAttnLd + c;
+        op16_t* dk = sK + r * kAttnLd + c;
+        op16_t* dv = sV + r * kAttnLd + c;
         if (r < S) {
-            const __nv_bfloat16* src = base + static_cast<size_t>(r) * ld + c;
+            const op16_t* src = base + static_cast<size_t>(r) * ld + c;
             cp_async_16(dk, src + H * kAttnDh);
             cp_async_16(dv, src + 2 * H * kAttnDh);
         } else {
@@ -93,8 +93,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
                         const int c = ks * 16 + (((lane >> 3) & 1) << 3);
                         uint32_t kf[4];
                         ldmatrix_x4(kf, smem_u32(sK + r * kAttnLd + c));
-                        mma_bf16_16816(s[np * 2], qf[ks], kf[0], kf[1]);
-                        mma_bf16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
+                        mma_op16_16816(s[np * 2], qf[ks], kf[0], kf[1]);
+                        mma_op16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
                     }
                 }
             }
@@ -141,10 +141,10 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
             for (int kp = 0; kp < 4; ++kp) {       // 16-key k-steps
                 if (kp * 2 < nkt) {
                     uint32_t pf[4];
-                    pf[0] = pack_bf16x2(s[kp * 2][0], s[kp * 2][1]);
-                    pf[1] = pack_bf16x2(s[kp * 2][2], s[kp * 2][3]);
-                    pf[2] = pack_bf16x2(s[kp * 2 + 1][0], s[kp * 2 + 1][1]);
-                    pf[3] = pack_bf16x2(s[kp * 2 + 1][2], s[kp * 2 + 1][3]);
+                    pf[0] = pack_op16x2(s[kp * 2][0], s[kp * 2][1]);
+                    pf[1] = pack_op16x2(s[kp * 2][2], s[kp * 2][3]);
+                    pf[2] = pack_op16x2(s[kp * 2 + 1][0], s[kp * 2 + 1][1]);
+                    pf[3] = pack_op16x2(s[kp * 2 + 1][2], s[kp * 2 + 1][3]);
 #pragma unroll
                     for (int dp = 0; dp < 4; ++dp) {   // pairs of 8-wide dh tiles
                         // ldmatrix x4 trans: (keys 0-7, dh 0-7), (keys 8-15, dh 0-7), (keys 0-7, dh 8-15), (keys 8-15, dh 8-15)
@@ -152,8 +152,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
                         const int c = dp * 16 + ((lane >> 4) << 3);
                         uint32_t vf[4];
                         ldmatrix_x4_trans(vf, smem_u32(sV + r * kAttnLd + c));
-                        mma_bf16_16816(o[dp * 2], pf, vf[0], vf[1]);
-                        mma_bf16_16816(o[dp * 2 + 1], pf, vf[2], vf[3]);
+                        mma_op16_16816(o[dp * 2], pf, vf[0], vf[1]);
+                        mma_op16_16816(o[dp * 2 + 1], pf, vf[2], vf[3]);
                     }
                 }
             }
@@ -165,16 +165,16 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        __nv_bfloat16* ob = out + static_cast<size_t>(img) * S * (H * kAttnDh) + h * kAttnDh;
+        op16_t* ob = out + static_cast<size_t>(img) * S * (H * kAttnDh) + h * kAttnDh;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             const int c = nt * 8 + tq * 2;
             if (row0 < S)
                 *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(row0) * (H * kAttnDh) + c) =
-                    pack_bf16x2(o[nt][0] * i0, o[nt][1] * i0);
+                    pack_op16x2(o[nt][0] * i0, o[nt][1] * i0);
             if (row1 < S)
                 *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(row1) * (H * kAttnDh) + c) =
-                    pack_bf16x2(o[nt][2] * i1, o[nt][3] * i1);
+                    pack_op16x2(o[nt][2] * i1, o[nt][3] * i1);
         }
     }
 }

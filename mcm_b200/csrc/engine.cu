@@ -1,6 +1,6 @@
 // mcm_b200 engine: the C ABI of include/mcm_b200.h on top of the sm_100a kernels in this directory.
 //
-// One handle = one CLIP vision tower resident on one B200: bf16 GEMM weights (fused QKV), fp32
+// One handle = one CLIP vision tower resident on one B200: fp16 GEMM weights (fused QKV), fp32
 // biases / LayerNorm / embeddings / projection / prompt bank, the activation workspace for
 // `max_batch` images and the TMA descriptors of every GEMM operand.  A forward is a fixed sequence
 // of launches on the caller's stream; nothing is allocated after mcm_create.
@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/mcm_b200.h"
+#include "attention_cls.cuh"
 #include "attention_mma.cuh"
 #include "gemm_tcgen05.cuh"
 #include "rowwise.cuh"
@@ -50,7 +51,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct LayerWeights {
-    __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    op16_t *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
     CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
@@ -66,7 +67,7 @@ struct McmHandle {
     std::string err;
 
     // weights
-    __nv_bfloat16* wpatch = nullptr;  // [D, Kp]
+    op16_t* wpatch = nullptr;  // [D, Kp]
     float *cls = nullptr, *pos = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr;
     float* wproj = nullptr;  // [P, D]
     std::vector<LayerWeights> layers;
@@ -82,9 +83,12 @@ struct McmHandle {
     int K = 0;
 
     // workspace
-    __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
+    op16_t *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
     float* x = nullptr;
+    float* x_cls = nullptr;                                   // [pad128(max_batch), D] CLS rows of the last layer
+    float *t_ln = nullptr, *t_feat = nullptr, *t_logit = nullptr;   // tail scratch: [max_batch, D | P | K]
     CUtensorMap tm_patches, tm_xn, tm_attn, tm_hid;
+    bool cls_shortcut = true;
 
     // host-stream path
     float* img_buf[2] = {nullptr, nullptr};
@@ -159,10 +163,10 @@ int make_tmap(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uin
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {cols * sizeof(__nv_bfloat16)};
+    cuuint64_t gstr[1] = {cols * sizeof(op16_t)};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -176,7 +180,7 @@ inline int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 template <int BN, int EPI>
 int launch_gemm_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     static bool attr_done = false;  // per instantiation; one device per process in practice
-    auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+    auto kern = gemm_f16_tn_kernel<BN, EPI>;
     if (!attr_done) {
         MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
         attr_done = true;
@@ -211,12 +215,12 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     ProfScope prof(h, prof_kind, st);
 #define MCM_GEMM_CASE(BN, E) \
     if (bn == BN && epi == E) return launch_gemm_t<BN, E>(h, ta, tb, p, st);
-    MCM_GEMM_CASE(256, EPI_BIAS_BF16)
-    MCM_GEMM_CASE(256, EPI_BIAS_QGELU_BF16)
+    MCM_GEMM_CASE(256, EPI_BIAS_F16)
+    MCM_GEMM_CASE(256, EPI_BIAS_QGELU_F16)
     MCM_GEMM_CASE(256, EPI_BIAS_RESID_F32)
     MCM_GEMM_CASE(256, EPI_POS_F32)
-    MCM_GEMM_CASE(128, EPI_BIAS_BF16)
-    MCM_GEMM_CASE(128, EPI_BIAS_QGELU_BF16)
+    MCM_GEMM_CASE(128, EPI_BIAS_F16)
+    MCM_GEMM_CASE(128, EPI_BIAS_QGELU_F16)
     MCM_GEMM_CASE(128, EPI_BIAS_RESID_F32)
     MCM_GEMM_CASE(128, EPI_POS_F32)
 #undef MCM_GEMM_CASE
@@ -239,14 +243,14 @@ int dispatch_vec(McmHandle* h, int D, F&& f) {
 }
 
 int launch_layernorm(McmHandle* h, const float* x, const float* g, const float* b, void* out, int M, int D, float eps,
-                     bool out_bf16, cudaStream_t st) {
+                     bool out_f16, cudaStream_t st) {
     if (M <= 0) return MCM_OK;
     if (D % 128 != 0) return fail(h, MCM_EUNSUPPORTED, "LayerNorm width %d is not a multiple of 128", D);
     const int grid = (M + (kRowThreads / 32) - 1) / (kRowThreads / 32);
     ProfScope prof(h, MCM_PROF_LAYERNORM, st);
     int rc = dispatch_vec(h, D, [&](auto vec) {
         constexpr int V = decltype(vec)::value;
-        if (out_bf16)
+        if (out_f16)
             layernorm_kernel<V, true><<<grid, kRowThreads, 0, st>>>(x, g, b, out, M, eps);
         else
             layernorm_kernel<V, false><<<grid, kRowThreads, 0, st>>>(x, g, b, out, M, eps);
@@ -258,10 +262,10 @@ int launch_layernorm(McmHandle* h, const float* x, const float* g, const float* 
     return MCM_OK;
 }
 
-int launch_attention(McmHandle* h, const __nv_bfloat16* qkv, __nv_bfloat16* out, int b, int S, int H, cudaStream_t st) {
+int launch_attention(McmHandle* h, const op16_t* qkv, op16_t* out, int b, int S, int H, cudaStream_t st) {
     if (b <= 0) return MCM_OK;
     const int keys_pad = (S + 15) / 16 * 16;
-    const size_t smem = static_cast<size_t>(2) * keys_pad * kAttnLd * sizeof(__nv_bfloat16);
+    const size_t smem = static_cast<size_t>(2) * keys_pad * kAttnLd * sizeof(op16_t);
     if (smem > 200 * 1024) return fail(h, MCM_EUNSUPPORTED, "sequence length %d too long for the attention kernel", S);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -280,22 +284,22 @@ int launch_attention(McmHandle* h, const __nv_bfloat16* qkv, __nv_bfloat16* out,
     return MCM_OK;
 }
 
-int launch_tail(McmHandle* h, const float* x, int b, float T, int kind, float* feats, float* scores, cudaStream_t st) {
+int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T, int kind, float* feats, float* scores,
+                cudaStream_t st) {
     if (b <= 0) return MCM_OK;
-    const int K = scores ? h->K : 0;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(kTailImgs) * (h->D + h->P + K) + 8 + kTailImgs);
-    if (smem > 220 * 1024) return fail(h, MCM_EUNSUPPORTED, "prompt bank with K=%d rows does not fit the tail kernel", K);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        MCM_CUDA(h, cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
-    const int grid = (b + kTailImgs - 1) / kTailImgs;
     ProfScope prof(h, MCM_PROF_TAIL, st);
-    tail_kernel<<<grid, kTailThreads, smem, st>>>(x, h->S, h->D, h->P, K, b, h->post_g, h->post_b, h->cfg.eps, h->wproj,
-                                                  h->bank, T, kind, feats, scores);
+    pooled_layernorm_kernel<<<(b + 7) / 8, 256, 0, st>>>(x, row_stride, h->D, b, h->post_g, h->post_b, h->cfg.eps, h->t_ln);
+    float* f = feats ? feats : h->t_feat;
+    dim3 g1((h->P + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
+    sgemm_tn_kernel<<<g1, 256, 0, st>>>(h->t_ln, h->wproj, f, b, h->P, h->D);
+    h->launches += 2;
+    if (scores) {
+        dim3 g2((h->K + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
+        sgemm_tn_kernel<<<g2, 256, 0, st>>>(f, h->bank, h->t_logit, b, h->K, h->P);
+        score_rows_kernel<<<(b + 7) / 8, 256, 0, st>>>(f, h->t_logit, h->P, h->K, b, T, kind, scores);
+        h->launches += 2;
+    }
     MCM_CUDA(h, cudaGetLastError());
-    h->launches++;
     return MCM_OK;
 }
 
@@ -325,19 +329,39 @@ int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
     return MCM_OK;
 }
 
-// embeddings + encoder; leaves the fp32 residual stream of the last layer in h->x
-int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st) {
+// embeddings + encoder.  Returns in *pooled / *pooled_stride where the rows the tail pools live:
+// the CLS rows of h->x (stride S * D) or, with the last-layer shortcut, the compact h->x_cls (stride D).
+int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st, const float** pooled, size_t* pooled_stride) {
     int rc = launch_embed(h, images, b, st);
     if (rc) return rc;
     const int M = b * h->S, D = h->D, F = h->F;
+    *pooled = h->x;
+    *pooled_stride = static_cast<size_t>(h->S) * D;
     for (int i = 0; i < h->L; ++i) {
         const LayerWeights& w = h->layers[i];
         // xn = LN1(x) is already in place (embed_finish for layer 0, end of the previous layer otherwise)
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xn, w.tm_wqkv, M, 3 * D, D, EPI_BIAS_BF16, w.bqkv, h->qkv, nullptr, nullptr, 0, 0, st))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xn, w.tm_wqkv, M, 3 * D, D, EPI_BIAS_F16, w.bqkv, h->qkv, nullptr, nullptr, 0, 0, st))) return rc;
+        if (i + 1 == h->L && h->cls_shortcut) {
+            // only query row 0 of every image is consumed after this point (HF:685)
+            {
+                ProfScope prof(h, MCM_PROF_ATTENTION, st);
+                attention_cls_kernel<<<(b * h->H + kClsWarps - 1) / kClsWarps, kClsWarps * 32, 0, st>>>(
+                    h->qkv, h->x, h->attn, h->x_cls, b, h->S, h->H, 0.125f);
+            }
+            MCM_CUDA(h, cudaGetLastError());
+            h->launches++;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st))) return rc;
+            if ((rc = launch_layernorm(h, h->x_cls, w.ln2g, w.ln2b, h->xn, b, D, h->cfg.eps, true, st))) return rc;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, b, F, D, EPI_BIAS_QGELU_F16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, b, D, F, EPI_BIAS_RESID_F32, w.b2, h->x_cls, h->x_cls, nullptr, 0, 0, st))) return rc;
+            *pooled = h->x_cls;
+            *pooled_stride = D;
+            break;
+        }
         if ((rc = launch_attention(h, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32, w.bo, h->x, h->x, nullptr, 0, 0, st))) return rc;
         if ((rc = launch_layernorm(h, h->x, w.ln2g, w.ln2b, h->xn, M, D, h->cfg.eps, true, st))) return rc;
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, M, F, D, EPI_BIAS_QGELU_BF16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, M, F, D, EPI_BIAS_QGELU_F16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, EPI_BIAS_RESID_F32, w.b2, h->x, h->x, nullptr, 0, 0, st))) return rc;
         if (i + 1 < h->L) {
             const LayerWeights& n = h->layers[i + 1];
@@ -371,7 +395,7 @@ int dev_alloc(McmHandle* h, T** p, size_t n, bool zero) {
 // where one HF tensor goes
 struct Dest {
     float* f32 = nullptr;            // fp32 destination, or
-    __nv_bfloat16* bf16 = nullptr;   // bf16 destination (converted)
+    op16_t* fp16 = nullptr;   // fp16 destination (converted)
     int64_t rows = 0;
     int cols = 0, dst_ld = 0;
     int slot = -1;
@@ -400,8 +424,8 @@ const char* kLayerNames[16] = {"layer_norm1.weight", "layer_norm1.bias", "layer_
 bool resolve_key(McmHandle* h, const char* key, Dest* d) {
     const int D = h->D, F = h->F, P = h->P;
     auto f32 = [&](float* p, int64_t n, int slot) { d->f32 = p; d->rows = 1; d->cols = (int)n; d->slot = slot; return true; };
-    auto b16 = [&](__nv_bfloat16* p, int64_t rows, int cols, int ld, int slot) {
-        d->bf16 = p; d->rows = rows; d->cols = cols; d->dst_ld = ld; d->slot = slot; return true;
+    auto b16 = [&](op16_t* p, int64_t rows, int cols, int ld, int slot) {
+        d->fp16 = p; d->rows = rows; d->cols = cols; d->dst_ld = ld; d->slot = slot; return true;
     };
     if (!strcmp(key, "vision_model.embeddings.class_embedding")) return f32(h->cls, D, SLOT_CLS);
     if (!strcmp(key, "vision_model.embeddings.patch_embedding.weight")) return b16(h->wpatch, D, h->Kpatch, h->Kp, SLOT_PATCH);
@@ -466,7 +490,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     if (cfg->heads <= 0 || cfg->width != cfg->heads * 64)
         return fail(nullptr, MCM_EUNSUPPORTED, "width / heads must be 64 (got %d / %d)", cfg->width, cfg->heads);
     if (cfg->mlp <= 0 || cfg->mlp % 128 != 0) return fail(nullptr, MCM_EUNSUPPORTED, "mlp %d must be a multiple of 128", cfg->mlp);
-    if (cfg->proj <= 0 || cfg->proj % 4 != 0) return fail(nullptr, MCM_EUNSUPPORTED, "proj %d must be a multiple of 4", cfg->proj);
+    if (cfg->proj <= 0 || cfg->proj % 16 != 0) return fail(nullptr, MCM_EUNSUPPORTED, "proj %d must be a multiple of 16", cfg->proj);
+    if (cfg->image_size / cfg->patch * (cfg->image_size / cfg->patch) + 1 > kClsMaxS)
+        return fail(nullptr, MCM_EUNSUPPORTED, "more than %d tokens per image are not supported", kClsMaxS);
     if (cfg->layers <= 0 || cfg->max_batch <= 0) return fail(nullptr, MCM_EINVAL, "layers and max_batch must be positive");
 
     int ndev = 0;
@@ -550,6 +576,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(dev_alloc(h, &h->qkv, (size_t)h->m_pad * 3 * D, true));
     MCM_TRY(dev_alloc(h, &h->attn, (size_t)h->m_pad * D, true));
     MCM_TRY(dev_alloc(h, &h->hid, (size_t)h->m_pad * F, true));
+    MCM_TRY(dev_alloc(h, &h->x_cls, (size_t)((cfg->max_batch + 127) / 128 * 128) * D, true));
+    MCM_TRY(dev_alloc(h, &h->t_ln, (size_t)cfg->max_batch * D, false));
+    MCM_TRY(dev_alloc(h, &h->t_feat, (size_t)cfg->max_batch * h->P, false));
     MCM_TRY(make_tmap(h, &h->tm_patches, h->patches, h->mp_pad, h->Kp, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_xn, h->xn, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_attn, h->attn, h->m_pad, D, kGemmBlockM));
@@ -571,6 +600,7 @@ void mcm_destroy(McmHandle* h) {
     }
     fr(h->stage); fr(h->bank); fr(h->patches); fr(h->x); fr(h->xn); fr(h->qkv); fr(h->attn); fr(h->hid);
     fr(h->img_buf[0]); fr(h->img_buf[1]); fr(h->scores_buf);
+    fr(h->x_cls); fr(h->t_ln); fr(h->t_feat); fr(h->t_logit);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -594,7 +624,7 @@ int mcm_load_weight(McmHandle* h, const char* key, const float* data, int64_t nu
         MCM_CUDA(h, cudaMemcpy(d.f32, data, want * sizeof(float), cudaMemcpyDefault));
     } else {
         MCM_CUDA(h, cudaMemcpy(h->stage, data, want * sizeof(float), cudaMemcpyDefault));
-        convert_rows_bf16_kernel<<<1024, 256>>>(h->stage, d.bf16, d.rows, d.cols, d.dst_ld);
+        convert_rows_f16_kernel<<<1024, 256>>>(h->stage, d.fp16, d.rows, d.cols, d.dst_ld);
         MCM_CUDA(h, cudaGetLastError());
         MCM_CUDA(h, cudaDeviceSynchronize());
     }
@@ -627,13 +657,13 @@ int mcm_finalize_weights(McmHandle* h) {
 int mcm_set_text_bank(McmHandle* h, const float* bank, int32_t K, int32_t already_unit) {
     if (!h || !bank) return fail(h, MCM_EINVAL, "mcm_set_text_bank: NULL argument");
     if (K <= 0) return fail(h, MCM_EINVAL, "K must be positive (got %d)", K);
-    const size_t smem = sizeof(float) * (static_cast<size_t>(kTailImgs) * (h->D + h->P + K) + 8 + kTailImgs);
-    if (smem > 220 * 1024) return fail(h, MCM_EUNSUPPORTED, "prompt bank with K=%d rows does not fit the tail kernel", K);
     MCM_CUDA(h, cudaSetDevice(h->cfg.device));
     MCM_CUDA(h, cudaDeviceSynchronize());
     if (h->bank) { cudaFree(h->bank); h->bank = nullptr; h->K = 0; }
+    if (h->t_logit) { cudaFree(h->t_logit); h->t_logit = nullptr; }
     int rc = dev_alloc(h, &h->bank, (size_t)K * h->P, false);
     if (rc) return rc;
+    if ((rc = dev_alloc(h, &h->t_logit, (size_t)h->cfg.max_batch * K, false))) return rc;
     MCM_CUDA(h, cudaMemcpy(h->bank, bank, (size_t)K * h->P * sizeof(float), cudaMemcpyDefault));
     if (!already_unit) {
         normalize_rows_kernel<<<(K + 7) / 8, 256>>>(h->bank, K, h->P);
@@ -650,8 +680,10 @@ int mcm_image_features(McmHandle* h, const float* images, int32_t b, float* feat
     if (b == 0) return MCM_OK;
     if (!images || !feats) return fail(h, MCM_EINVAL, "mcm_image_features: NULL buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = forward_tower(h, images, b, st))) return rc;
-    return launch_tail(h, h->x, b, 1.0f, SCORE_MCM, feats, nullptr, st);
+    const float* pooled = nullptr;
+    size_t stride = 0;
+    if ((rc = forward_tower(h, images, b, st, &pooled, &stride))) return rc;
+    return launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, feats, nullptr, st);
 }
 
 int mcm_score(McmHandle* h, const float* images, int32_t b, float T, int32_t kind, float* scores, void* stream) {
@@ -662,8 +694,10 @@ int mcm_score(McmHandle* h, const float* images, int32_t b, float T, int32_t kin
     if (!(T > 0.f)) return fail(h, MCM_EINVAL, "temperature must be positive (got %g)", (double)T);
     if (kind < MCM_SCORE_MCM || kind > MCM_SCORE_VAR) return fail(h, MCM_EINVAL, "unknown score kind %d", kind);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = forward_tower(h, images, b, st))) return rc;
-    return launch_tail(h, h->x, b, T, kind, nullptr, scores, st);
+    const float* pooled = nullptr;
+    size_t stride = 0;
+    if ((rc = forward_tower(h, images, b, st, &pooled, &stride))) return rc;
+    return launch_tail(h, pooled, stride, b, T, kind, nullptr, scores, st);
 }
 
 int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int32_t batch, float T, int32_t kind,
@@ -714,6 +748,14 @@ int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int
 int64_t mcm_launch_count(const McmHandle* h) { return h ? h->launches : 0; }
 void mcm_reset_launch_count(McmHandle* h) { if (h) h->launches = 0; }
 
+int mcm_set_option(McmHandle* h, int32_t option, int32_t value) {
+    if (!h) return MCM_EINVAL;
+    switch (option) {
+        case MCM_OPT_CLS_SHORTCUT: h->cls_shortcut = value != 0; return MCM_OK;
+        default: return fail(h, MCM_EINVAL, "unknown option %d", option);
+    }
+}
+
 int mcm_profile_enable(McmHandle* h, int32_t on) {
     if (!h) return MCM_EINVAL;
     h->prof_on = on != 0;
@@ -758,14 +800,14 @@ int mcm_dbg_gemm(McmHandle* h, const void* a, const void* w, const float* bias, 
 }
 
 int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float* b, void* out, int32_t M, int32_t D,
-                      float eps, int32_t out_bf16, void* stream) {
+                      float eps, int32_t out_f16, void* stream) {
     if (!h || !x || !g || !b || !out) return fail(h, MCM_EINVAL, "mcm_dbg_layernorm: NULL argument");
-    return launch_layernorm(h, x, g, b, out, M, D, eps, out_bf16 != 0, static_cast<cudaStream_t>(stream));
+    return launch_layernorm(h, x, g, b, out, M, D, eps, out_f16 != 0, static_cast<cudaStream_t>(stream));
 }
 
 int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t S, int32_t H, void* stream) {
     if (!h || !qkv || !o) return fail(h, MCM_EINVAL, "mcm_dbg_attention: NULL argument");
-    return launch_attention(h, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(o), b, S, H,
+    return launch_attention(h, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -773,7 +815,7 @@ int mcm_dbg_tail(McmHandle* h, const float* x, int32_t b, float T, int32_t kind,
     int rc = check_ready(h, b, scores != nullptr);
     if (rc) return rc;
     if (!x) return fail(h, MCM_EINVAL, "mcm_dbg_tail: NULL argument");
-    return launch_tail(h, x, b, T, kind, feats, scores, static_cast<cudaStream_t>(stream));
+    return launch_tail(h, x, static_cast<size_t>(h->S) * h->D, b, T, kind, feats, scores, static_cast<cudaStream_t>(stream));
 }
 
 int mcm_dbg_embed(McmHandle* h, const float* images, int32_t b, float* x, void* stream) {

@@ -1,6 +1,6 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:   C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+// Persistent, warp-specialised fp16 GEMM for sm_100a:   C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
 //
-//   * A (activations) and W (nn.Linear weight, [out,in]) are both K-major bf16 in HBM.
+//   * A (activations) and W (nn.Linear weight, [out,in]) are both K-major fp16 in HBM.
 //   * TMA (cp.async.bulk.tensor, 128-byte swizzle) stages 128 x 64 A tiles and BLOCK_N x 64 W
 //     tiles into a shared-memory ring; one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16,
 //     fp32 accumulation in TMEM); four epilogue warps drain TMEM with tcgen05.ld and apply the fused
@@ -17,8 +17,8 @@
 namespace mcm {
 
 enum GemmEpilogue : int {
-    EPI_BIAS_BF16 = 0,        // out_bf16 = acc + bias                               (QKV projection)
-    EPI_BIAS_QGELU_BF16 = 1,  // out_bf16 = quick_gelu(acc + bias)                    (fc1, HF activations.py:117-123)
+    EPI_BIAS_F16 = 0,        // out_f16 = acc + bias                               (QKV projection)
+    EPI_BIAS_QGELU_F16 = 1,  // out_f16 = quick_gelu(acc + bias)                    (fc1, HF activations.py:117-123)
     EPI_BIAS_RESID_F32 = 2,   // out_f32  = resid_f32 + acc + bias  (in place ok)     (out_proj / fc2 + residual)
     EPI_POS_F32 = 3,          // out_f32[b*S + 1 + p] = acc + pos[1 + p]               (patch embedding, no bias)
 };
@@ -30,7 +30,7 @@ struct GemmParams {
     int m_valid;        // rows >= m_valid are computed but never stored
     int ldo;            // leading dimension (elements) of out / resid
     const float* bias;  // [N] (unused for EPI_POS_F32)
-    void* out;          // bf16 or fp32
+    void* out;          // fp16 or fp32
     const float* resid; // EPI_BIAS_RESID_F32
     const float* pos;   // EPI_POS_F32: position embedding [S, N]
     int np;             // EPI_POS_F32: patches per image
@@ -38,7 +38,7 @@ struct GemmParams {
 };
 
 constexpr int kGemmBlockM = 128;
-constexpr int kGemmBlockK = 64;    // 64 bf16 = one 128-byte swizzle row
+constexpr int kGemmBlockK = 64;    // 64 fp16 = one 128-byte swizzle row
 constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 template <int BLOCK_N>
@@ -54,7 +54,7 @@ struct GemmSmem {
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int m, int n) {
     // this thread owns row m, columns [n, n+32)
-    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
+    if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
         uint32_t packed[16];
 #pragma unroll
@@ -64,17 +64,17 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
             float v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
             float v2 = __uint_as_float(acc[4 * j + 2]) + b.z;
             float v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
-            if constexpr (EPI == EPI_BIAS_QGELU_BF16) {
+            if constexpr (EPI == EPI_BIAS_QGELU_F16) {
                 v0 = __fdividef(v0, 1.0f + __expf(-1.702f * v0));
                 v1 = __fdividef(v1, 1.0f + __expf(-1.702f * v1));
                 v2 = __fdividef(v2, 1.0f + __expf(-1.702f * v2));
                 v3 = __fdividef(v3, 1.0f + __expf(-1.702f * v3));
             }
-            packed[2 * j + 0] = pack_bf16x2(v0, v1);
-            packed[2 * j + 1] = pack_bf16x2(v2, v3);
+            packed[2 * j + 0] = pack_op16x2(v0, v1);
+            packed[2 * j + 1] = pack_op16x2(v2, v3);
         }
         if (m < p.m_valid) {
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.ldo + n);
+            uint4* o = reinterpret_cast<uint4*>(static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + n);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 o[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
@@ -121,7 +121,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
     using L = GemmSmem<BLOCK_N>;
     constexpr int kStages = L::kStages;
@@ -182,7 +182,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N);
+            constexpr uint32_t idesc = make_idesc_f16(kGemmBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -199,7 +199,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint64_t bdesc = make_smem_desc_sw128(sa + L::kABytes, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                        // +32 bytes (16 bf16) along K inside the swizzle atom == +2 in the 16-byte address field
+                        // +32 bytes (16 fp16) along K inside the swizzle atom == +2 in the 16-byte address field
                         umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);

@@ -67,15 +67,15 @@ struct WarpRow {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) d4[i * 32 + lane] = v[i];
     }
-    __device__ __forceinline__ void store_bf16(__nv_bfloat16* __restrict__ dst, int lane) const {
+    __device__ __forceinline__ void store_f16(op16_t* __restrict__ dst, int lane) const {
         uint2* d2 = reinterpret_cast<uint2*>(dst);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) d2[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        for (int i = 0; i < VEC; ++i) d2[i * 32 + lane] = make_uint2(pack_op16x2(v[i].x, v[i].y), pack_op16x2(v[i].z, v[i].w));
     }
 };
 
-// x f32 [M, D] -> LayerNorm -> bf16 or f32 [M, D]
-template <int VEC, bool OUT_BF16>
+// x f32 [M, D] -> LayerNorm -> fp16 or f32 [M, D]
+template <int VEC, bool OUT_F16>
 __global__ void __launch_bounds__(kRowThreads)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  void* __restrict__ out, int M, float eps) {
@@ -86,8 +86,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     WarpRow<VEC> r;
     r.load(x + static_cast<size_t>(row) * D, lane);
     r.layernorm(gamma, beta, eps, lane);
-    if constexpr (OUT_BF16)
-        r.store_bf16(static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(row) * D, lane);
+    if constexpr (OUT_F16)
+        r.store_f16(static_cast<op16_t*>(out) + static_cast<size_t>(row) * D, lane);
     else
         r.store_f32(static_cast<float*>(out) + static_cast<size_t>(row) * D, lane);
 }
@@ -95,10 +95,10 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // Finish the embeddings after the patch GEMM has written  patch . W + pos  into the patch rows of x:
 //   row b*S      <- class_embedding + pos[0]                    (HF:212-213,217)
 //   every row    <- pre_layrnorm(row)                            (HF:677)   -> x   (fp32 residual stream)
-//   and          <- layer_norm1 of layer 0 applied on top        (HF:371)   -> xn  (bf16 GEMM operand)
+//   and          <- layer_norm1 of layer 0 applied on top        (HF:371)   -> xn  (fp16 GEMM operand)
 template <int VEC>
 __global__ void __launch_bounds__(kRowThreads)
-embed_finish_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xn, const float* __restrict__ cls,
+embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xn, const float* __restrict__ cls,
                     const float* __restrict__ pos, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
                     const float* __restrict__ ln1_g, const float* __restrict__ ln1_b, int M, int S, float eps) {
     constexpr int D = 128 * VEC;
@@ -116,24 +116,24 @@ embed_finish_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xn, const
     r.store_f32(x + static_cast<size_t>(row) * D, lane);
     if (xn != nullptr) {
         r.layernorm(ln1_g, ln1_b, eps, lane);
-        r.store_bf16(xn + static_cast<size_t>(row) * D, lane);
+        r.store_f16(xn + static_cast<size_t>(row) * D, lane);
     }
 }
 
 // Patch gather ("im2col" of the stride = kernel = patch conv, HF:148-154,209-210):
-//   images f32 [b, 3, H, W] NCHW  ->  patches bf16 [b * G * G, Kp],  column = c * p * p + i * p + j
+//   images f32 [b, 3, H, W] NCHW  ->  patches fp16 [b * G * G, Kp],  column = c * p * p + i * p + j
 // (the flattening order of the conv weight [D, 3, p, p]); columns >= 3 p^2 (K padding) are never
 // written and stay zero.  One CTA copies the 3 * p image rows that make up one row of G patches:
 // reads are contiguous 224-float image rows, writes are p-element runs.
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches, int G, int p, int Kp) {
+patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp) {
     const int W = G * p;
     const int gy = blockIdx.x % G;
     const int b = blockIdx.x / G;
     const int half_w = W >> 1;
     const int n = 3 * p * half_w;  // float2 items in this patch row
     const float* src_img = img + static_cast<size_t>(b) * 3 * W * W;
-    __nv_bfloat16* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
+    op16_t* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const int xh = t % half_w;
         const int ci = t / half_w;  // c * p + i
@@ -143,19 +143,19 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patch
         const float2 v = __ldg(reinterpret_cast<const float2*>(src_img + (static_cast<size_t>(c) * W + gy * p + i) * W + x));
         const int gx = x / p;
         const int j = x - gx * p;
-        *reinterpret_cast<uint32_t*>(dst_row + static_cast<size_t>(gx) * Kp + (c * p + i) * p + j) = pack_bf16x2(v.x, v.y);
+        *reinterpret_cast<uint32_t*>(dst_row + static_cast<size_t>(gx) * Kp + (c * p + i) * p + j) = pack_op16x2(v.x, v.y);
     }
 }
 
-// fp32 -> bf16 with row re-striding (weight packing): dst[r * dst_ld + c] = src[r * cols + c]
-__global__ void convert_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
+// fp32 -> fp16 with row re-striding (weight packing): dst[r * dst_ld + c] = src[r * cols + c]
+__global__ void convert_rows_f16_kernel(const float* __restrict__ src, op16_t* __restrict__ dst, int64_t rows,
                                          int cols, int dst_ld) {
     const int64_t total = rows * cols;
     for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = t / cols;
         const int c = static_cast<int>(t - r * cols);
-        dst[r * dst_ld + c] = __float2bfloat16_rn(src[t]);
+        dst[r * dst_ld + c] = to_op16(src[t]);
     }
 }
 

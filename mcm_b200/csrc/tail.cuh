@@ -6,172 +6,136 @@
 // :233-248 (score reductions).  The reference ships the whole [B,K] softmax to the host and
 // reduces there; here only [B] scores leave the kernel.
 //
-// One CTA scores kTailImgs images so every projection / bank row read from L2 is reused kTailImgs
-// times; warps stride over output rows, lanes over the contraction dimension (float4, coalesced),
-// warp-shuffle reductions finish each dot product.
+// Four small launches: pooled LayerNorm (one warp per image), two fp32 CUDA-core GEMMs (projection,
+// cosine logits), and a one-warp-per-image reduction kernel (warp-shuffle max / sum-exp).
 #pragma once
 #include "ptx.cuh"
 
 namespace mcm {
 
-constexpr int kTailImgs = 4;
-constexpr int kTailThreads = 256;
 
 enum ScoreKind : int { SCORE_MCM = 0, SCORE_MAX_LOGIT = 1, SCORE_ENERGY = 2, SCORE_ENTROPY = 3, SCORE_VAR = 4 };
 
-__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
-    // red: >= 8 floats of scratch; returns the reduction to every thread
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    v = is_max ? warp_max(v) : warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float r = red[0];
-#pragma unroll
-    for (int i = 1; i < kTailThreads / 32; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
-    return r;
+// ---- stage 1: post_layernorm of the pooled rows: x row (img * row_stride) -> ln [b, D] ----
+__global__ void __launch_bounds__(256)
+pooled_layernorm_kernel(const float* __restrict__ x, size_t row_stride, int D, int b, const float* __restrict__ g,
+                        const float* __restrict__ be, float eps, float* __restrict__ ln) {
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (img >= b) return;
+    const float* row = x + static_cast<size_t>(img) * row_stride;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += row[c];
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float d = row[c] - mean;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    for (int c = lane; c < D; c += 32)
+        ln[static_cast<size_t>(img) * D + c] = (row[c] - mean) * rstd * __ldg(g + c) + __ldg(be + c);
 }
 
-// smem layout (floats): ln[kTailImgs][D] | feat[kTailImgs][P] | z[kTailImgs][K] | red[8] | inv_norm[kTailImgs]
-__global__ void __launch_bounds__(kTailThreads)
-tail_kernel(const float* __restrict__ x, int S, int D, int P, int K, int b, const float* __restrict__ post_g,
-            const float* __restrict__ post_b, float eps, const float* __restrict__ wproj /*[P,D]*/,
-            const float* __restrict__ bank /*[K,P] unit rows*/, float T, int kind, float* __restrict__ feats,
-            float* __restrict__ scores) {
-    extern __shared__ float tsm[];
-    float* s_ln = tsm;
-    float* s_feat = s_ln + kTailImgs * D;
-    float* s_z = s_feat + kTailImgs * P;
-    float* s_red = s_z + kTailImgs * K;
-    float* s_inv = s_red + 8;
+// ---- stages 2, 3: C[M, N] = A[M, Kd] . B[N, Kd]^T in fp32 on the CUDA cores ----
+// (visual_projection: [b, D] x [P, D]^T; cosine logits: [b, P] x [K, P]^T.  0.5 GFLOP per 256 images;
+// fp32 keeps the tail exact to the reference's own arithmetic.)  64 x 64 x 16 tiles, 256 threads,
+// 4 x 4 outputs per thread, operands transposed through shared memory.
+constexpr int kSgemmTile = 64, kSgemmK = 16;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NW = kTailThreads / 32;
-    const int img0 = blockIdx.x * kTailImgs;
-    const int nimg = min(kTailImgs, b - img0);
+__global__ void __launch_bounds__(256)
+sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int Kd) {
+    __shared__ float sA[kSgemmK][kSgemmTile + 4];
+    __shared__ float sB[kSgemmK][kSgemmTile + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * kSgemmTile, n0 = blockIdx.x * kSgemmTile;
+    const int lr = tid >> 2;         // 0..63: tile row this thread loads
+    const int lc = (tid & 3) * 4;    // 0,4,8,12: k offset of its float4
+    const int ty = tid >> 4, tx = tid & 15;   // 16 x 16 thread grid, 4 x 4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const bool a_ok = (m0 + lr) < M, b_ok = (n0 + lr) < N;
+    const float* ap = A + static_cast<size_t>(m0 + lr) * Kd + lc;
+    const float* bp = B + static_cast<size_t>(n0 + lr) * Kd + lc;
+    for (int k0 = 0; k0 < Kd; k0 += kSgemmK) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+        if (a_ok) av = *reinterpret_cast<const float4*>(ap + k0);
+        if (b_ok) bv = __ldg(reinterpret_cast<const float4*>(bp + k0));
+        __syncthreads();
+        sA[lc + 0][lr] = av.x; sA[lc + 1][lr] = av.y; sA[lc + 2][lr] = av.z; sA[lc + 3][lr] = av.w;
+        sB[lc + 0][lr] = bv.x; sB[lc + 1][lr] = bv.y; sB[lc + 2][lr] = bv.z; sB[lc + 3][lr] = bv.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSgemmK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) C[static_cast<size_t>(m) * N + n] = acc[i][j];
+        }
+    }
+}
 
-    // ---- post_layernorm of the CLS rows (one warp per image) ----
-    for (int i = warp; i < kTailImgs; i += NW) {
-        float* dst = s_ln + i * D;
-        if (i < nimg) {
-            const float* row = x + static_cast<size_t>(img0 + i) * S * D;
-            float s = 0.f;
-            for (int c = lane; c < D; c += 32) s += row[c];
-            const float mean = warp_sum(s) / D;
-            float q = 0.f;
-            for (int c = lane; c < D; c += 32) {
-                const float d = row[c] - mean;
-                q += d * d;
+// ---- stage 4: one warp per image: 1 / ||feat||, z = logits / ||feat||, score reductions (:226, :233-248) ----
+__global__ void __launch_bounds__(256)
+score_rows_kernel(const float* __restrict__ feats, const float* __restrict__ logits, int P, int K, int b, float T,
+                  int kind, float* __restrict__ scores) {
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (img >= b) return;
+    const float* f = feats + static_cast<size_t>(img) * P;
+    float q = 0.f;
+    for (int c = lane; c < P; c += 32) q += f[c] * f[c];
+    const float inv = 1.0f / sqrtf(warp_sum(q));
+    const float* z = logits + static_cast<size_t>(img) * K;
+    float m = -INFINITY;
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, z[k] * inv);
+    m = warp_max(m);
+    float out;
+    if (kind == SCORE_MAX_LOGIT) {
+        out = -m;
+    } else {
+        const float invT = 1.0f / T;
+        float se = 0.f, sez = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float d = (z[k] * inv - m) * invT;
+            const float e = expf(d);
+            se += e;
+            sez += e * d;
+        }
+        se = warp_sum(se);
+        if (kind == SCORE_MCM) {
+            out = -1.0f / se;  // max_k softmax = exp(0) / sum
+        } else if (kind == SCORE_ENERGY) {
+            out = -T * (m * invT + logf(se));
+        } else if (kind == SCORE_ENTROPY) {
+            out = logf(se) - warp_sum(sez) / se;  // -sum p log p
+        } else {  // SCORE_VAR: -mean_k (p_k - 1/K)^2  (np.var; second pass avoids cancellation)
+            const float mp = 1.0f / K, inv_se = 1.0f / se;
+            float dv = 0.f;
+            for (int k = lane; k < K; k += 32) {
+                const float pk = expf((z[k] * inv - m) * invT) * inv_se - mp;
+                dv += pk * pk;
             }
-            const float rstd = rsqrtf(warp_sum(q) / D + eps);
-            for (int c = lane; c < D; c += 32) dst[c] = (row[c] - mean) * rstd * __ldg(post_g + c) + __ldg(post_b + c);
-        } else {
-            for (int c = lane; c < D; c += 32) dst[c] = 0.f;
+            out = -warp_sum(dv) / K;
         }
     }
-    __syncthreads();
-
-    // ---- visual projection: feat[i][p] = sum_d ln[i][d] * W[p][d] ----
-    const int D4 = D >> 2;
-    for (int p = warp; p < P; p += NW) {
-        const float4* w4 = reinterpret_cast<const float4*>(wproj + static_cast<size_t>(p) * D);
-        float acc[kTailImgs];
-#pragma unroll
-        for (int i = 0; i < kTailImgs; ++i) acc[i] = 0.f;
-        for (int c = lane; c < D4; c += 32) {
-            const float4 w = __ldg(w4 + c);
-#pragma unroll
-            for (int i = 0; i < kTailImgs; ++i) {
-                const float4 a = reinterpret_cast<const float4*>(s_ln + i * D)[c];
-                acc[i] += (a.x * w.x + a.y * w.y) + (a.z * w.z + a.w * w.w);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kTailImgs; ++i) acc[i] = warp_sum(acc[i]);
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < kTailImgs; ++i) s_feat[i * P + p] = acc[i];
-        }
-    }
-    __syncthreads();
-
-    if (feats != nullptr) {
-        for (int t = threadIdx.x; t < nimg * P; t += kTailThreads) feats[static_cast<size_t>(img0) * P + t] = s_feat[t];
-    }
-    if (scores == nullptr) return;
-
-    // ---- 1 / ||feat||  (utils/detection_util.py:226) ----
-    for (int i = warp; i < kTailImgs; i += NW) {
-        float q = 0.f;
-        for (int c = lane; c < P; c += 32) q += s_feat[i * P + c] * s_feat[i * P + c];
-        q = warp_sum(q);
-        if (lane == 0) s_inv[i] = (i < nimg) ? 1.0f / sqrtf(q) : 0.f;
-    }
-    __syncthreads();
-
-    // ---- cosine logits z[i][k] = (feat[i] . bank[k]) / ||feat[i]||   (:232) ----
-    const int P4 = P >> 2;
-    for (int k = warp; k < K; k += NW) {
-        const float4* t4 = reinterpret_cast<const float4*>(bank + static_cast<size_t>(k) * P);
-        float acc[kTailImgs];
-#pragma unroll
-        for (int i = 0; i < kTailImgs; ++i) acc[i] = 0.f;
-        for (int c = lane; c < P4; c += 32) {
-            const float4 w = __ldg(t4 + c);
-#pragma unroll
-            for (int i = 0; i < kTailImgs; ++i) {
-                const float4 a = reinterpret_cast<const float4*>(s_feat + i * P)[c];
-                acc[i] += (a.x * w.x + a.y * w.y) + (a.z * w.z + a.w * w.w);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kTailImgs; ++i) acc[i] = warp_sum(acc[i]);
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < kTailImgs; ++i) s_z[i * K + k] = acc[i] * s_inv[i];
-        }
-    }
-    __syncthreads();
-
-    // ---- score reductions over k (:233-248) ----
-    const float invT = 1.0f / T;
-    for (int i = 0; i < nimg; ++i) {
-        const float* z = s_z + i * K;
-        float m = -INFINITY;
-        for (int k = threadIdx.x; k < K; k += kTailThreads) m = fmaxf(m, z[k]);
-        m = block_reduce(m, s_red, true);
-        float out;
-        if (kind == SCORE_MAX_LOGIT) {
-            out = -m;
-        } else {
-            float se = 0.f, sez = 0.f;
-            for (int k = threadIdx.x; k < K; k += kTailThreads) {
-                const float d = (z[k] - m) * invT;
-                const float e = expf(d);
-                se += e;
-                sez += e * d;
-            }
-            se = block_reduce(se, s_red, false);
-            if (kind == SCORE_MCM) {
-                out = -1.0f / se;  // max_k softmax = exp(0) / sum
-            } else if (kind == SCORE_ENERGY) {
-                out = -T * (m * invT + logf(se));
-            } else if (kind == SCORE_ENTROPY) {
-                sez = block_reduce(sez, s_red, false);
-                out = logf(se) - sez / se;  // -sum p log p
-            } else {  // SCORE_VAR: -mean_k (p_k - 1/K)^2  (np.var; second pass avoids cancellation)
-                const float mp = 1.0f / K, inv_se = 1.0f / se;
-                float dv = 0.f;
-                for (int k = threadIdx.x; k < K; k += kTailThreads) {
-                    const float pk = expf((z[k] - m) * invT) * inv_se - mp;
-                    dv += pk * pk;
-                }
-                dv = block_reduce(dv, s_red, false);
-                out = -dv / K;
-            }
-        }
-        if (threadIdx.x == 0) scores[img0 + i] = out;
-    }
+    if (lane == 0) scores[img] = out;
 }
 
 // bank rows /= ||row||   (utils/detection_util.py:231); one warp per row

@@ -129,5 +129,26 @@ def test_launch_count(tiny_net):
     eng.reset_launch_count()
     eng.score(torch.zeros(3, 3, 224, 224, device="cuda"))
     torch.cuda.synchronize()
-    # patchify + patch GEMM + embed_finish + L * (3 GEMM... ) : 3 + 7 L - 1 + tail
-    assert eng.launch_count == 3 + 7 * cfg.layers - 1 + 1
+    # 3 embedding launches + 6 per layer + (L - 1) next-layer LayerNorms + 4 tail launches
+    assert eng.launch_count == 7 * cfg.layers + 6
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "small"])
+def test_cls_shortcut_is_equivalent(engine_factory, cfg_name):
+    """The last-layer CLS-only shortcut (HF:685 consumes only row 0) must not change results beyond
+    the rounding of one fp16 attention output."""
+    from mcm_b200 import synth
+    eng, sd, cfg = engine_factory(cfg_name, 5, 32)
+    eng.set_text_bank(synth.synth_unit_bank(12, cfg.proj, 9))
+    x = torch.from_numpy(synth.synth_images(11, 8)).cuda()
+    try:
+        eng.set_cls_shortcut(True)
+        a_s, a_f = eng.score(x).clone(), eng.image_features(x).clone()
+        eng.set_cls_shortcut(False)
+        b_s, b_f = eng.score(x).clone(), eng.image_features(x).clone()
+    finally:
+        eng.set_cls_shortcut(True)
+    torch.cuda.synchronize()
+    rel = ((a_f - b_f).norm(dim=1) / b_f.norm(dim=1)).max().item()
+    assert rel <= 2e-3, rel
+    assert (a_s - b_s).abs().max().item() <= 2e-5

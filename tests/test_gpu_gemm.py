@@ -1,5 +1,5 @@
 """tcgen05 GEMM (TMA -> smem ring -> tcgen05.mma -> TMEM -> fused epilogue) vs torch fp32 of the
-same bf16 operands.  Replaces the nn.Linear SGEMMs of HF CLIP (modeling_clip.py:310-312,334,348-350)."""
+same fp16 operands.  Replaces the nn.Linear SGEMMs of HF CLIP (modeling_clip.py:310-312,334,348-350)."""
 import pytest
 import torch
 
@@ -32,16 +32,16 @@ SHAPES = [
 def test_gemm_matches_torch(engine_factory, M, N, K, epi):
     eng, _, _ = engine_factory("tiny", 5, 8)
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
-    a = (torch.randn(M, K, device="cuda", generator=g)).to(torch.bfloat16)
-    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    a = (torch.randn(M, K, device="cuda", generator=g)).to(torch.float16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.float16)
     bias = torch.randn(N, device="cuda", generator=g)
     resid = torch.randn(M, N, device="cuda", generator=g) if epi == 2 else None
     out = eng.dbg_gemm(a, w, bias, resid, epi)
     torch.cuda.synchronize()
     ref = _ref(a, w, bias, resid, epi)
     err = (out.float() - ref).abs().max().item()
-    # fp32 accumulation of exact bf16 products: only the summation order and (epi 0/1) the final
-    # bf16 rounding of |values| <~ 8 differ
+    # fp32 accumulation of exact fp16 products: only the summation order and (epi 0/1) the final
+    # fp16 rounding of |values| <~ 8 differ
     tol = 2e-3 if epi == 2 else 6e-2
     assert err <= tol, f"M={M} N={N} K={K} epi={epi}: max|d|={err}"
     if epi != 2:
@@ -53,8 +53,8 @@ def test_gemm_in_place_residual(engine_factory):
     eng, _, _ = engine_factory("tiny", 5, 8)
     g = torch.Generator(device="cuda").manual_seed(1)
     M, N, K = 640, 256, 512
-    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
-    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.float16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.float16)
     bias = torch.randn(N, device="cuda", generator=g)
     x = torch.randn(M, N, device="cuda", generator=g)
     ref = _ref(a, w, bias, x.clone(), 2)

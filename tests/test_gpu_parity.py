@@ -3,7 +3,7 @@
 Golden fixtures (tests/golden/*.npz) hold the outputs of the UNMODIFIED reference
 ``get_ood_scores_clip`` + ``get_measures`` run on CPU in the authoring container
 (oracle/make_golden.py); inputs are regenerated here from the stored seeds.  The north-star
-tolerance is |d score| <= 1e-3 per image (fp32 reference vs bf16-operand tensor cores with fp32
+tolerance is |d score| <= 1e-3 per image (fp32 reference vs fp16-operand tensor cores with fp32
 accumulation / residual / LayerNorm / softmax) and AUROC / FPR95 within 0.05 pt; FPR95 moves in
 steps of 1/n_ood, so on the small fixtures the bound is the larger of 0.05 pt and 1.5 steps, and
 the 0.05 pt bound proper is checked at full stream size in test_fullsize_stream_metrics.
@@ -59,7 +59,7 @@ def test_golden_scores_and_metrics(case, golden_dir):
                 assert d_fpr <= max(5e-4, 1.5 / n_ood), (case, sc, m_got, m_ref)
             else:
                 # random-init text bank: every image has nearly the same cosines, the score spread
-                # (std ~1e-5) is comparable to bf16 rounding, so AUROC here measures noise ordering;
+                # (std ~1e-5) is comparable to fp16 rounding, so AUROC here measures noise ordering;
                 # only a loose sanity bound applies
                 assert d_auroc <= 0.05, (case, sc, m_got, m_ref)
     finally:

@@ -34,8 +34,8 @@ def run_case(i):
         m = torch.zeros(K, device="cuda")
         m[16 * ks:16 * ks + 16] = 1
         a = a * m
-    a = a.to(torch.bfloat16)
-    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    a = a.to(torch.float16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.float16)
     bias = torch.zeros(N, device="cuda")
     resid = torch.zeros(M, N, device="cuda") if epi == 2 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
