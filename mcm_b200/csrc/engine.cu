@@ -25,6 +25,7 @@
 #include "attention_cls.cuh"
 #include "attention_mma.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2cta.cuh"
 #include "rowwise.cuh"
 #include "tail.cuh"
 
@@ -63,6 +64,7 @@ struct McmHandle {
     McmConfig cfg{};
     int G = 0, Np = 0, S = 0, D = 0, H = 0, F = 0, P = 0, L = 0, Kp = 0, Kpatch = 0;
     int num_sms = 0;
+    bool gemm_1cta = false;  // debug A/B switch (env MCM_GEMM_1CTA=1): single-CTA 128 x BLOCK_N tiles instead of CTA pairs
     int64_t m_pad = 0, mp_pad = 0;  // padded token rows / patch rows for max_batch
     std::string err;
 
@@ -193,6 +195,22 @@ int launch_gemm_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, co
     return MCM_OK;
 }
 
+template <int BN, int EPI>
+int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    static bool attr_done = false;
+    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI>;
+    if (!attr_done) {
+        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
+        attr_done = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int clusters = std::min(tiles, h->num_sms / 2);
+    kern<<<2 * clusters, kGemm2Threads, Gemm2Smem<BN>::kTotal, st>>>(ta, tb, p);
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
 // C[M, N] = A[M, K] W[N, K]^T with fused epilogue.  M rows valid; A's tensor map covers >= ceil(M/128)*128 rows.
 int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi,
                 const float* bias, void* out, const float* resid, const float* pos, int np, int seq, cudaStream_t st) {
@@ -213,8 +231,10 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     p.np = np;
     p.seq = seq;
     ProfScope prof(h, prof_kind, st);
-#define MCM_GEMM_CASE(BN, E) \
-    if (bn == BN && epi == E) return launch_gemm_t<BN, E>(h, ta, tb, p, st);
+    if (!h->gemm_1cta) p.m_tiles = (M + kGemm2TileM - 1) / kGemm2TileM;
+#define MCM_GEMM_CASE(BN, E)                                                     \
+    if (bn == BN && epi == E)                                                    \
+        return h->gemm_1cta ? launch_gemm_t<BN, E>(h, ta, tb, p, st) : launch_gemm2_t<BN, E>(h, ta, tb, p, st);
     MCM_GEMM_CASE(256, EPI_BIAS_F16)
     MCM_GEMM_CASE(256, EPI_BIAS_QGELU_F16)
     MCM_GEMM_CASE(256, EPI_BIAS_RESID_F32)
@@ -270,6 +290,9 @@ int launch_attention(McmHandle* h, const op16_t* qkv, op16_t* out, int b, int S,
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         MCM_CUDA(h, cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // without this the driver's default L1/shared split leaves room for ONE 60 KB CTA per SM
+        MCM_CUDA(h, cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
         attr_smem = smem;
     }
     const int mtiles = (S + 15) / 16;
@@ -521,8 +544,12 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     h->L = cfg->layers;
     h->Kpatch = 3 * cfg->patch * cfg->patch;
     h->Kp = (h->Kpatch + kGemmBlockK - 1) / kGemmBlockK * kGemmBlockK;
-    h->m_pad = (static_cast<int64_t>(cfg->max_batch) * h->S + 127) / 128 * 128;
-    h->mp_pad = (static_cast<int64_t>(cfg->max_batch) * h->Np + 127) / 128 * 128;
+    h->m_pad = (static_cast<int64_t>(cfg->max_batch) * h->S + 255) / 256 * 256;
+    h->mp_pad = (static_cast<int64_t>(cfg->max_batch) * h->Np + 255) / 256 * 256;
+    {
+        const char* e = getenv("MCM_GEMM_1CTA");
+        h->gemm_1cta = e && e[0] == '1';
+    }
     const int D = h->D, F = h->F;
 
 #define MCM_TRY(expr)               \
@@ -557,13 +584,14 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         MCM_TRY(dev_alloc(h, &w.ln1b, D, false));
         MCM_TRY(dev_alloc(h, &w.ln2g, D, false));
         MCM_TRY(dev_alloc(h, &w.ln2b, D, false));
-        const uint32_t bnD = gemm_block_n(D), bn3D = gemm_block_n(3 * D), bnF = gemm_block_n(F);
+        const uint32_t wdiv = h->gemm_1cta ? 1 : 2;   // CTA pairs load half of the W tile each
+        const uint32_t bnD = gemm_block_n(D) / wdiv, bn3D = gemm_block_n(3 * D) / wdiv, bnF = gemm_block_n(F) / wdiv;
         MCM_TRY(make_tmap(h, &w.tm_wqkv, w.wqkv, 3 * D, D, bn3D));
         MCM_TRY(make_tmap(h, &w.tm_wo, w.wo, D, D, bnD));
         MCM_TRY(make_tmap(h, &w.tm_w1, w.w1, F, D, bnF));
         MCM_TRY(make_tmap(h, &w.tm_w2, w.w2, D, F, bnD));
     }
-    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D)));
+    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D) / (h->gemm_1cta ? 1 : 2)));
     h->loaded.assign(SLOT_GLOBALS + 16 * h->L, 0);
     h->stage_elems = (size_t)std::max(std::max((size_t)F * D, (size_t)D * h->Kpatch), std::max((size_t)h->S * D, (size_t)h->P * D));
     MCM_TRY(dev_alloc(h, &h->stage, h->stage_elems, false));
@@ -576,7 +604,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(dev_alloc(h, &h->qkv, (size_t)h->m_pad * 3 * D, true));
     MCM_TRY(dev_alloc(h, &h->attn, (size_t)h->m_pad * D, true));
     MCM_TRY(dev_alloc(h, &h->hid, (size_t)h->m_pad * F, true));
-    MCM_TRY(dev_alloc(h, &h->x_cls, (size_t)((cfg->max_batch + 127) / 128 * 128) * D, true));
+    MCM_TRY(dev_alloc(h, &h->x_cls, (size_t)((cfg->max_batch + 255) / 256 * 256) * D, true));
     MCM_TRY(dev_alloc(h, &h->t_ln, (size_t)cfg->max_batch * D, false));
     MCM_TRY(dev_alloc(h, &h->t_feat, (size_t)cfg->max_batch * h->P, false));
     MCM_TRY(make_tmap(h, &h->tm_patches, h->patches, h->mp_pad, h->Kp, kGemmBlockM));
@@ -795,7 +823,7 @@ int mcm_dbg_gemm(McmHandle* h, const void* a, const void* w, const float* bias, 
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
-    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N)))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / (h->gemm_1cta ? 1 : 2)))) return rc;
     return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, epi, bias, out, resid, nullptr, 0, 0, static_cast<cudaStream_t>(stream));
 }
 

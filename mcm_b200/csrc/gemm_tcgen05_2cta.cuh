@@ -1,0 +1,293 @@
+// Persistent, warp-specialised fp16 GEMM for sm_100a on CTA PAIRS (tcgen05 cta_group::2):
+//     C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   * A (activations) and W (nn.Linear weight [out,in]) are K-major fp16 in HBM.
+//   * The grid is one 2-CTA cluster per SM pair (TPC), persistent over 256 x BLOCK_N output tiles.
+//     Each CTA of the pair TMA-loads ITS 128 rows of A and ITS HALF (BLOCK_N / 2 rows) of W per
+//     64-wide k-block (128-byte swizzle) into a shared-memory ring; the leader CTA's elected thread
+//     issues tcgen05.mma.cta_group::2 (UMMA 256 x BLOCK_N x 16): both tensor cores read A from their
+//     own SM and the two W halves from both SMs, so each SM stages and reads half the W bytes a
+//     single-CTA 128 x BLOCK_N tile would need -- the shared-memory bandwidth that capped the 1-CTA
+//     kernel (TMA writes + UMMA reads > 128 B/clk/SM) is no longer the limiter.
+//   * fp32 accumulators live in TMEM (each CTA holds its 128 rows x BLOCK_N columns), two stages, so
+//     the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * Epilogue warps drain TMEM with tcgen05.ld, transpose 32 x 32 chunks through padded shared
+//     memory and read/write HBM with fully coalesced 128-bit accesses (4 rows x 128 B per warp
+//     instruction) while applying bias / quick_gelu / residual / position-embedding fusions.
+//
+// Barrier protocol (leader = cluster rank 0):
+//   full[s]   (leader's)    1 arrival (leader producer, expect_tx = both CTAs' bytes) + TMA bytes of both CTAs
+//   empty[s]  (each CTA's)  tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full[a]  (each)    tcgen05.commit multicast after the last k-block of a tile
+//   tmem_empty[a] (leader's) 8 arrivals: 4 epilogue warps x 2 CTAs (remote arrive from rank 1)
+//
+// Replaces the cuBLAS SGEMM calls behind nn.Linear in HF CLIP:
+//   q/k/v_proj HF:modeling_clip.py:310-312, out_proj :334, fc1/fc2 :348-350, patch conv :148-154.
+#pragma once
+#include <cuda.h>
+#include "gemm_tcgen05.cuh"
+#include "ptx.cuh"
+
+namespace mcm {
+
+constexpr int kGemm2Threads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
+constexpr int kStgLd = 36;           // staging row stride in floats (32 + 4: conflict-free 16-byte rows)
+
+template <int BLOCK_N>
+struct Gemm2Smem {
+    static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
+    static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+    static constexpr int kStagingBytes = 4 * 32 * kStgLd * 4;             // 4 epilogue warps
+    static constexpr int kBarrierBytes = 1024;
+    static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /* alignment slack */;
+};
+
+// ---- cluster / 2-CTA PTX ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2D tiled load into THIS CTA's smem; the byte count is signalled on `bar_cluster_addr`, a
+// shared::cluster mbarrier address that may live in the peer (leader) CTA.
+__device__ __forceinline__ void tma_load_2d_cta2(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int32_t c0,
+                                                 int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_cta2(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_cta2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cta2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
+// One 32-row x 32-column chunk of the accumulator, owned row-per-thread in `acc`, leaves through a
+// padded smem transpose so that global accesses are 4 rows x 128 B (fp32) or 4 rows x 64 B (fp16)
+// per warp instruction.  m_base: global row of this warp's first row; n: first column of the chunk.
+template <int EPI>
+__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float* stg, const uint32_t (&acc)[32], int m_base,
+                                                     int n, int lane) {
+    float4* w = reinterpret_cast<float4*>(stg + lane * kStgLd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        w[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                           __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+    const int cq = lane & 7;       // this lane's 4-column group
+    const int r0 = lane >> 3;      // rows r0, r0 + 4, ..., r0 + 28
+    const int col = n + 4 * cq;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (EPI != EPI_POS_F32) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 4 * i;
+        const int m = m_base + r;
+        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgLd + 4 * cq);
+        if (m < p.m_valid) {
+            if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16) {
+                v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                if constexpr (EPI == EPI_BIAS_QGELU_F16) {
+                    v.x = __fdividef(v.x, 1.0f + __expf(-1.702f * v.x));
+                    v.y = __fdividef(v.y, 1.0f + __expf(-1.702f * v.y));
+                    v.z = __fdividef(v.z, 1.0f + __expf(-1.702f * v.z));
+                    v.w = __fdividef(v.w, 1.0f + __expf(-1.702f * v.w));
+                }
+                *reinterpret_cast<uint2*>(static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col) =
+                    make_uint2(pack_op16x2(v.x, v.y), pack_op16x2(v.z, v.w));
+            } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                const float4 rs = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
+                v.x = rs.x + (v.x + bias.x); v.y = rs.y + (v.y + bias.y);
+                v.z = rs.z + (v.z + bias.z); v.w = rs.w + (v.w + bias.w);
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + col) = v;
+            } else {  // EPI_POS_F32: patch row m of image b -> token row b * seq + 1 + patch, plus its position embedding
+                const int b = m / p.np;
+                const int pi = m - b * p.np;
+                const float4 e = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.ldo + col));
+                v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (static_cast<size_t>(b) * p.seq + 1 + pi) * p.ldo + col) = v;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// p.m_tiles here counts 256-row cluster tiles.
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const GemmParams p) {
+    using L = Gemm2Smem<BLOCK_N>;
+    constexpr int kStages = L::kStages;
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
+    static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + kStages * L::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes + L::kStagingBytes);
+    uint64_t* full_bar = bars;                      // [kStages]
+    uint64_t* empty_bar = bars + kStages;           // [kStages]
+    uint64_t* tmem_full = bars + 2 * kStages;       // [2]
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_cta2<kTmemCols>(tmem_ptr);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===== TMA producer (both CTAs): own A rows, own half of W; bytes land on the leader's full barrier =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = tile / p.n_tiles;
+                const int n_blk = tile - m_blk * p.n_tiles;
+                const int a_row = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM;
+                const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::kStageBytes;
+                    uint8_t* sb = sa + L::kABytes;
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                    tma_load_2d_cta2(sa, &tmap_a, bar, kb * kGemmBlockK, a_row);
+                    tma_load_2d_cta2(sb, &tmap_b, bar, kb * kGemmBlockK, b_row);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one()) {
+            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc = make_idesc_f16(kGemm2TileM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(sa + L::kABytes, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < kGemmBlockK / 16; ++k)
+                        umma_f16_cta2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_cta2_mc(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_cta2_mc(&tmem_full[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs): TMEM -> registers -> smem transpose -> coalesced HBM =====
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        float* stg = staging + quad * 32 * kStgLd;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / p.n_tiles;
+            const int n_blk = tile - m_blk * p.n_tiles;
+            const int m_base = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
+            mbar_wait(&tmem_full[as], aphase);
+            tcgen05_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
+            if (m_base < p.m_valid) {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(t_row + c, acc);
+                    tmem_ld_wait();
+                    gemm2_epilogue_chunk<EPI>(p, stg, acc, m_base, n_blk * BLOCK_N + c, lane);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tmem_empty[as]);
+                else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    __syncwarp();
+    tcgen05_fence_before();
+    cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still signal its barriers
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc_cta2<kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace mcm

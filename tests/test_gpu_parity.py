@@ -131,6 +131,12 @@ def test_fullsize_stream_metrics():
                     ref.append(O.ood_scores(torch.from_numpy(x).cuda(), sd_gpu, cfg, bank_t, T=1, score="MCM", batch=125))
             res[name] = (np.concatenate(got), np.concatenate(ref))
         err = max(np.abs(res["id"][0] - res["id"][1]).max(), np.abs(res["ood"][0] - res["ood"][1]).max())
+        try:   # keep the raw vectors for offline analysis of the metric sensitivity
+            import helpers
+            np.savez_compressed(os.path.join(helpers.REPORT_DIR, "fullsize_scores.npz"), id_got=res["id"][0],
+                                id_ref=res["id"][1], ood_got=res["ood"][0], ood_ref=res["ood"][1])
+        except OSError:
+            pass
         m_got = DU.get_measures(-res["id"][0], -res["ood"][0])
         m_ref = O.get_measures(-res["id"][1], -res["ood"][1])
         report("fullsize", dict(n=n, K=K, max_abs_err=float(err), score_std=float(res["id"][1].std()),
