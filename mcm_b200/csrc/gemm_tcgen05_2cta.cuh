@@ -19,7 +19,7 @@
 //   full[s]   (leader's)    1 arrival (leader producer, expect_tx = both CTAs' bytes) + TMA bytes of both CTAs
 //   empty[s]  (each CTA's)  tcgen05.commit multicast from the leader's MMA thread
 //   tmem_full[a]  (each)    tcgen05.commit multicast after the last k-block of a tile
-//   tmem_empty[a] (leader's) 8 arrivals: 4 epilogue warps x 2 CTAs (remote arrive from rank 1)
+//   tmem_empty[a] (leader's) 16 arrivals: 8 epilogue warps x 2 CTAs (remote arrive from rank 1)
 //
 // Replaces the cuBLAS SGEMM calls behind nn.Linear in HF CLIP:
 //   q/k/v_proj HF:modeling_clip.py:310-312, out_proj :334, fc1/fc2 :348-350, patch conv :148-154.
@@ -30,7 +30,8 @@
 
 namespace mcm {
 
-constexpr int kGemm2Threads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kGemm2Threads = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kGemm2EpiWarps = 8;    // two per TMEM lane quadrant (= per SM sub-partition): one column half each
 constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
 constexpr int kStgLd = 36;           // staging row stride in floats (32 + 4: conflict-free 16-byte rows)
 
@@ -39,8 +40,8 @@ struct Gemm2Smem {
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
-    static constexpr int kStagingBytes = 4 * 32 * kStgLd * 4;             // 4 epilogue warps
+    static constexpr int kStages = (BLOCK_N == 256) ? 5 : 7;
+    static constexpr int kStagingBytes = kGemm2EpiWarps * 32 * kStgLd * 4;
     static constexpr int kBarrierBytes = 1024;
     static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /* alignment slack */;
 };
@@ -102,23 +103,43 @@ __device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar) {
         : "memory");
 }
 
-// One 32-row x 32-column chunk of the accumulator, owned row-per-thread in `acc`, leaves through a
-// padded smem transpose so that global accesses are 4 rows x 128 B (fp32) or 4 rows x 64 B (fp16)
-// per warp instruction.  m_base: global row of this warp's first row; n: first column of the chunk.
+// One 32-row x 32-column chunk of the accumulator leaves through a padded smem transpose so that
+// global accesses are 4 rows x 128 B (fp32) or 4 rows x 64 B (fp16) per warp instruction.
+// All global reads of the chunk (residual rows / position rows) are issued BEFORE the TMEM load and
+// the transpose so their latency overlaps them.  t_addr: TMEM address (lane quadrant + column) of the
+// chunk; m_base: global row of this warp's first row; col0: first global column of the chunk.
 template <int EPI>
-__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float* stg, const uint32_t (&acc)[32], int m_base,
-                                                     int n, int lane) {
+__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float* stg, uint32_t t_addr, int m_base, int col0,
+                                                     int lane, const float4 bias) {
+    const int cq = lane & 7;       // this lane's 4-column group
+    const int r0 = lane >> 3;      // rows r0, r0 + 4, ..., r0 + 28
+    const int col = col0 + 4 * cq;
+    float4 side[8];                // residual (EPI 2) or position-embedding (EPI 3) values
+    size_t orow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m_base + r0 + 4 * i;
+        side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        orow[i] = static_cast<size_t>(m);
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            if (m < p.m_valid) side[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
+        } else if constexpr (EPI == EPI_POS_F32) {
+            // patch row m of image b -> token row b * seq + 1 + patch, plus its position embedding
+            const int b = m / p.np;
+            const int pi = m - b * p.np;
+            orow[i] = static_cast<size_t>(b) * p.seq + 1 + pi;
+            if (m < p.m_valid) side[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.ldo + col));
+        }
+    }
+    uint32_t acc[32];
+    tmem_ld_32x32b_x32(t_addr, acc);
+    tmem_ld_wait();
     float4* w = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         w[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
                            __uint_as_float(acc[4 * j + 3]));
     __syncwarp();
-    const int cq = lane & 7;       // this lane's 4-column group
-    const int r0 = lane >> 3;      // rows r0, r0 + 4, ..., r0 + 28
-    const int col = n + 4 * cq;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (EPI != EPI_POS_F32) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + 4 * i;
@@ -133,19 +154,15 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float*
                     v.z = __fdividef(v.z, 1.0f + __expf(-1.702f * v.z));
                     v.w = __fdividef(v.w, 1.0f + __expf(-1.702f * v.w));
                 }
-                *reinterpret_cast<uint2*>(static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col) =
+                *reinterpret_cast<uint2*>(static_cast<op16_t*>(p.out) + orow[i] * p.ldo + col) =
                     make_uint2(pack_op16x2(v.x, v.y), pack_op16x2(v.z, v.w));
             } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-                const float4 rs = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
-                v.x = rs.x + (v.x + bias.x); v.y = rs.y + (v.y + bias.y);
-                v.z = rs.z + (v.z + bias.z); v.w = rs.w + (v.w + bias.w);
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + col) = v;
-            } else {  // EPI_POS_F32: patch row m of image b -> token row b * seq + 1 + patch, plus its position embedding
-                const int b = m / p.np;
-                const int pi = m - b * p.np;
-                const float4 e = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.ldo + col));
-                v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (static_cast<size_t>(b) * p.seq + 1 + pi) * p.ldo + col) = v;
+                v.x = side[i].x + (v.x + bias.x); v.y = side[i].y + (v.y + bias.y);
+                v.z = side[i].z + (v.z + bias.z); v.w = side[i].w + (v.w + bias.w);
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow[i] * p.ldo + col) = v;
+            } else {  // EPI_POS_F32
+                v.x += side[i].x; v.y += side[i].y; v.z += side[i].z; v.w += side[i].w;
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow[i] * p.ldo + col) = v;
             }
         }
     }
@@ -188,7 +205,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);
+            mbar_init(&tmem_empty[i], 2 * kGemm2EpiWarps);
         }
         fence_barrier_init();
     }
@@ -250,25 +267,32 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
     } else {
         // ===== epilogue warps (both CTAs): TMEM -> registers -> smem transpose -> coalesced HBM =====
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        float* stg = staging + quad * 32 * kStgLd;
+        const int ew = warp - 2;
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;           // which half of the tile's columns this warp drains
+        constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
+        float* stg = staging + ew * 32 * kStgLd;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = tile / p.n_tiles;
             const int n_blk = tile - m_blk * p.n_tiles;
             const int m_base = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
+            const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
+            float4 bias[kChunks];
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                bias[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (EPI != EPI_POS_F32)
+                    bias[c] = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + c * 32 + 4 * (lane & 7)));
+            }
             mbar_wait(&tmem_full[as], aphase);
             tcgen05_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
             if (m_base < p.m_valid) {
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
-                    uint32_t acc[32];
-                    tmem_ld_32x32b_x32(t_row + c, acc);
-                    tmem_ld_wait();
-                    gemm2_epilogue_chunk<EPI>(p, stg, acc, m_base, n_blk * BLOCK_N + c, lane);
-                }
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c)
+                    gemm2_epilogue_chunk<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias[c]);
             }
             tcgen05_fence_before();
             __syncwarp();
