@@ -1,0 +1,314 @@
+// Multi-head self-attention core on the 5th-gen tensor cores:  softmax(Q K^T / 8) V  per (image, head)
+// for sequences of up to 256 tokens (ViT-B/16: 197, ViT-B/32: 50), head dim 64, no mask, not causal
+// (HF:modeling_clip.py:261-279 eager == what SDPA computes, :318-331).
+//
+// Persistent CTAs (one per SM) walk over (image, head) items; every item is cut into 128-query-row
+// units.  Warp roles:
+//   warp 0      TMA producer: K and V of the item ([keys_pad x 64] fp16 boxes, 128-byte swizzle, 2-stage
+//               ring) and the Q tile of every unit (3-stage ring), straight out of the fused QKV buffer.
+//   warp 1      MMA issuer (one elected thread):  S = Q K^T   as UMMA 128 x keys_pad x 16 (x4, SS mode),
+//                                                 O = P V     as UMMA 128 x 64 x 16 (x keys_pad/16, TS mode:
+//               P is read from TENSOR MEMORY, V from shared memory as an MN-major operand).
+//   warps 2-9   two softmax groups of 4 warps; group g owns TMEM buffer g (256 columns), one thread per
+//               query row: row max and exp2 in fp32 straight from TMEM (tcgen05.ld), P written back over
+//               the dead S columns as fp16 (tcgen05.st), then O / rowsum -> fp16 -> smem transpose ->
+//               coalesced 128-byte row stores.  While one group runs its softmax the tensor core serves
+//               the other group's QK^T / PV, so the MUFU (exp2) pipe -- the real bound of this kernel:
+//               2 x 128 x keys_pad exponentials per item vs 16 per clock per SM -- stays busy.
+// TMEM map of buffer g (base = g * 256 columns):  S fp32 [0, keys_pad)  ->  P fp16 [0, keys_pad/2)
+//                                                 O fp32 [128, 192)  (dead S columns by the time PV runs)
+// Padded keys (>= S) are masked to probability 0; padded query rows are computed and never stored.
+//
+// qkv: fp16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)
+// out: fp16 [b * S, H * 64]      (== attn_output.transpose(1,2).reshape(B,S,D), HF:333)
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace mcm {
+
+constexpr int kAtcThreads = 320;
+constexpr int kAtcQStages = 3;
+constexpr int kAtcQBytes = 128 * 128;          // 128 rows x 64 fp16
+constexpr int kAtcStagingBytes = 8 * 32 * 128; // 8 softmax warps x 32 rows x 64 fp16
+
+struct AtcParams {
+    int b, S, H, keys_pad;   // keys_pad: S rounded up to 16 (<= 256)
+    int units_per_item;      // ceil(S / 128)
+    float scale_log2e;       // dh^-0.5 * log2(e)
+    op16_t* out;
+};
+
+__host__ __device__ inline int atc_smem_bytes(int keys_pad) {
+    return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
+}
+
+// ---- extra tcgen05 PTX ----
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                         const AtcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kv_bytes = p.keys_pad * 128;                       // one K or V tile
+    uint8_t* s_q = smem;                                         // [kAtcQStages][16 KB]
+    uint8_t* s_kv = smem + kAtcQStages * kAtcQBytes;             // [2][K | V]
+    uint8_t* s_stage = s_kv + 4 * kv_bytes;                      // [8 warps][32 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kAtcStagingBytes);
+    uint64_t* q_full = bars;                       // [3]
+    uint64_t* q_empty = bars + kAtcQStages;        // [3]
+    uint64_t* kv_full = bars + 2 * kAtcQStages;    // [2]
+    uint64_t* kv_empty = kv_full + 2;              // [2]
+    uint64_t* s_full = kv_full + 4;                // [2]  MMA -> softmax group: S ready
+    uint64_t* p_full = kv_full + 6;                // [2]  softmax group -> MMA: P written
+    uint64_t* o_full = kv_full + 8;                // [2]  MMA -> softmax group: O ready
+    uint64_t* s_free = kv_full + 10;               // [2]  softmax group -> MMA: O drained, buffer reusable
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(kv_full + 12);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = p.b * p.H;
+    const int upi = p.units_per_item;
+    const int D = p.H * 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+        for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===== TMA producer =====
+            uint32_t ic = 0, uc = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+                const int img = item / p.H, h = item - img * p.H;
+                const int row0 = img * p.S;
+                const int kvs = ic & 1;
+                mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes);
+                uint8_t* sk = s_kv + kvs * 2 * kv_bytes;
+                tma_load_2d(sk, &tmap_kv, &kv_full[kvs], D + h * 64, row0);
+                tma_load_2d(sk + kv_bytes, &tmap_kv, &kv_full[kvs], 2 * D + h * 64, row0);
+                for (int mt = 0; mt < upi; ++mt, ++uc) {
+                    const int qs = uc % kAtcQStages;
+                    mbar_wait(&q_empty[qs], ((uc / kAtcQStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[qs], kAtcQBytes);
+                    tma_load_2d(s_q + qs * kAtcQBytes, &tmap_q, &q_full[qs], h * 64, row0 + mt * 128);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ===== MMA issuer =====
+            const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+            const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
+            const uint32_t idesc_qk = make_idesc_f16(128, static_cast<uint32_t>(p.keys_pad));
+            const uint32_t idesc_pv = make_idesc_f16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
+            const int ksteps = p.keys_pad >> 4;
+            auto issue_qk = [&](uint32_t v) {
+                const uint32_t iv = v / upi;                      // CTA-local item index of unit v
+                const int kvs = iv & 1, qs = v % kAtcQStages, buf = v & 1;
+                mbar_wait(&kv_full[kvs], (iv >> 1) & 1);
+                mbar_wait(&q_full[qs], (v / kAtcQStages) & 1);
+                tcgen05_fence_after();
+                const uint64_t adesc = make_smem_desc_sw128(smem_u32(s_q + qs * kAtcQBytes), 16, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes), 16, 1024);
+                const uint32_t d = tmem_base + buf * 256;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+                umma_commit(&q_empty[qs]);
+                umma_commit(&s_full[buf]);
+            };
+            if (n_units > 0) issue_qk(0);
+            if (n_units > 1) issue_qk(1);
+            for (uint32_t u = 0; u < n_units; ++u) {
+                const int buf = u & 1;
+                const uint32_t iu = u / upi;
+                const int kvs = iu & 1;
+                mbar_wait(&p_full[buf], (u >> 1) & 1);
+                tcgen05_fence_after();
+                // V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
+                const uint64_t vdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes + kv_bytes), 1024, 1024);
+                const uint32_t d = tmem_base + buf * 256 + 128;
+                const uint32_t a = tmem_base + buf * 256;
+                for (int k = 0; k < ksteps; ++k) umma_f16_ts(d, a + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
+                umma_commit(&o_full[buf]);
+                if ((u + 1) % upi == 0) umma_commit(&kv_empty[kvs]);   // last unit of the item: K / V stage reusable
+                if (u + 2 < n_units) {
+                    mbar_wait(&s_free[buf], (u >> 1) & 1);
+                    tcgen05_fence_after();
+                    issue_qk(u + 2);
+                }
+            }
+        }
+    } else {
+        // ===== softmax / epilogue groups =====
+        const int g = (warp - 2) >> 2;       // group = TMEM buffer
+        const int quad = warp & 3;           // TMEM lane quadrant
+        const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t t_s = tmem_base + t_lane + g * 256;
+        uint8_t* stg = s_stage + (warp - 2) * 32 * 128;
+        const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+        const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
+        const int nfull = p.keys_pad >> 5;
+        const bool rem16 = (p.keys_pad & 16) != 0;
+        const float c = p.scale_log2e;
+        for (uint32_t u = g; u < n_units; u += 2) {
+            const uint32_t j = u >> 1;
+            const uint32_t iu = u / upi;
+            const int mt = static_cast<int>(u - iu * upi);
+            const int item = static_cast<int>(blockIdx.x) + static_cast<int>(iu) * static_cast<int>(gridDim.x);
+            const int img = item / p.H, h = item - img * p.H;
+            const int wrow0 = mt * 128 + quad * 32;       // first query row (within the image) of this warp
+            const bool warp_valid = wrow0 < p.S;
+            mbar_wait(&s_full[g], j & 1);
+            tcgen05_fence_after();
+            float row_sum = 1.f;
+            if (warp_valid) {
+                // ---- pass 1: row max over the S valid keys ----
+                float mx = -INFINITY;
+                for (int ch = 0; ch < nfull; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (ch * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
+                }
+                if (rem16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (nfull * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
+                }
+                const float mc = mx * c;
+                // ---- pass 2: p = exp2(s * c - max * c); P (fp16) overwrites the first half of the S columns ----
+                float sum = 0.f;
+                for (int ch = 0; ch < nfull; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int k0 = ch * 32 + 2 * e;
+                        const float p0 = (k0 < p.S) ? exp2f(__uint_as_float(v[2 * e]) * c - mc) : 0.f;
+                        const float p1 = (k0 + 1 < p.S) ? exp2f(__uint_as_float(v[2 * e + 1]) * c - mc) : 0.f;
+                        sum += p0 + p1;
+                        pk[e] = pack_op16x2(p0, p1);
+                    }
+                    tmem_st_32x32b_x16(t_s + ch * 16, pk);
+                }
+                if (rem16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
+                    tmem_ld_wait();
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k0 = nfull * 32 + 2 * e;
+                        const float p0 = (k0 < p.S) ? exp2f(__uint_as_float(v[2 * e]) * c - mc) : 0.f;
+                        const float p1 = (k0 + 1 < p.S) ? exp2f(__uint_as_float(v[2 * e + 1]) * c - mc) : 0.f;
+                        sum += p0 + p1;
+                        pk[e] = pack_op16x2(p0, p1);
+                    }
+                    tmem_st_32x32b_x8(t_s + nfull * 16, pk);
+                }
+                tmem_st_wait();
+                row_sum = sum;
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+
+            // ---- O = P V is computed by the tensor core; scale by 1 / rowsum and store ----
+            mbar_wait(&o_full[g], j & 1);
+            tcgen05_fence_after();
+            if (warp_valid) {
+                const float inv = 1.0f / row_sum;
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_s + 128 + hc * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {     // 4 x 16-byte chunks (8 fp16) of this half row
+                        uint4 w;
+                        w.x = pack_op16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+                        w.y = pack_op16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+                        w.z = pack_op16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+                        w.w = pack_op16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+                        const int chunk = hc * 4 + q;
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = w;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);     // TMEM buffer may be overwritten by the next QK^T
+            if (warp_valid) {
+                const int cq = lane & 7;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (lane >> 3) + 4 * i;
+                    const int row = wrow0 + r;
+                    if (row < p.S) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(stg + r * 128 + ((cq ^ (r & 7)) << 4));
+                        *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(img) * p.S + row) * D + h * 64 + cq * 8) = w;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    __syncwarp();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace mcm

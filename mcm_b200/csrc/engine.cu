@@ -24,6 +24,7 @@
 #include "../../include/mcm_b200.h"
 #include "attention_cls.cuh"
 #include "attention_mma.cuh"
+#include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "rowwise.cuh"
@@ -90,6 +91,8 @@ struct McmHandle {
     float* x_cls = nullptr;                                   // [pad128(max_batch), D] CLS rows of the last layer
     float *t_ln = nullptr, *t_feat = nullptr, *t_logit = nullptr;   // tail scratch: [max_batch, D | P | K]
     CUtensorMap tm_patches, tm_xn, tm_attn, tm_hid;
+    CUtensorMap tm_qkv_q, tm_qkv_kv;   // attention: 128-row Q boxes / keys_pad-row K,V boxes over the fused QKV buffer
+    bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
     bool cls_shortcut = true;
 
     // host-stream path
@@ -282,8 +285,7 @@ int launch_layernorm(McmHandle* h, const float* x, const float* g, const float* 
     return MCM_OK;
 }
 
-int launch_attention(McmHandle* h, const op16_t* qkv, op16_t* out, int b, int S, int H, cudaStream_t st) {
-    if (b <= 0) return MCM_OK;
+int launch_attention_mma(McmHandle* h, const op16_t* qkv, op16_t* out, int b, int S, int H, cudaStream_t st) {
     const int keys_pad = (S + 15) / 16 * 16;
     const size_t smem = static_cast<size_t>(2) * keys_pad * kAttnLd * sizeof(op16_t);
     if (smem > 200 * 1024) return fail(h, MCM_EUNSUPPORTED, "sequence length %d too long for the attention kernel", S);
@@ -302,6 +304,34 @@ int launch_attention(McmHandle* h, const op16_t* qkv, op16_t* out, int b, int S,
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
     attention_mma_kernel<<<b * H, nwarps * 32, smem, st>>>(qkv, out, S, H, keys_pad, scale_log2e);
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+// tq / tkv: tensor maps over the fused QKV buffer with 128-row and keys_pad-row boxes
+int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const op16_t* qkv, op16_t* out, int b, int S,
+                     int H, cudaStream_t st) {
+    if (b <= 0) return MCM_OK;
+    if (h->attn_mma || S > 256) return launch_attention_mma(h, qkv, out, b, S, H, st);
+    AtcParams p{};
+    p.b = b;
+    p.S = S;
+    p.H = H;
+    p.keys_pad = (S + 15) / 16 * 16;
+    p.units_per_item = (S + 127) / 128;
+    p.scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
+    p.out = out;
+    const int smem = atc_smem_bytes(p.keys_pad);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        MCM_CUDA(h, cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const int items = b * H;
+    const int grid = items < h->num_sms ? items : h->num_sms;
+    ProfScope prof(h, MCM_PROF_ATTENTION, st);
+    attention_tcgen05_kernel<<<grid, kAtcThreads, smem, st>>>(tq, tkv, p);
     MCM_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCM_OK;
@@ -381,7 +411,7 @@ int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st, con
             *pooled_stride = D;
             break;
         }
-        if ((rc = launch_attention(h, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
+        if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32, w.bo, h->x, h->x, nullptr, 0, 0, st))) return rc;
         if ((rc = launch_layernorm(h, h->x, w.ln2g, w.ln2b, h->xn, M, D, h->cfg.eps, true, st))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, M, F, D, EPI_BIAS_QGELU_F16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
@@ -611,6 +641,14 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(make_tmap(h, &h->tm_xn, h->xn, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_attn, h->attn, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_hid, h->hid, h->m_pad, F, kGemmBlockM));
+    {
+        const char* e = getenv("MCM_ATTN_MMA");
+        h->attn_mma = e && e[0] == '1';
+        if (h->S <= 256) {
+            MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
+            MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, (h->S + 15) / 16 * 16));
+        }
+    }
 #undef MCM_TRY
     *out = h;
     return MCM_OK;
@@ -835,7 +873,14 @@ int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float*
 
 int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t S, int32_t H, void* stream) {
     if (!h || !qkv || !o) return fail(h, MCM_EINVAL, "mcm_dbg_attention: NULL argument");
-    return launch_attention(h, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
+    if (b <= 0 || S <= 0 || H <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_attention: b, S, H must be positive");
+    CUtensorMap tq, tkv;
+    if (S <= 256 && !h->attn_mma) {
+        int rc;
+        if ((rc = make_tmap(h, &tq, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 128))) return rc;
+        if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, (S + 15) / 16 * 16))) return rc;
+    }
+    return launch_attention(h, tq, tkv, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
                             static_cast<cudaStream_t>(stream));
 }
 

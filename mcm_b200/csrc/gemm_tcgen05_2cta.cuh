@@ -11,7 +11,7 @@
 //     kernel (TMA writes + UMMA reads > 128 B/clk/SM) is no longer the limiter.
 //   * fp32 accumulators live in TMEM (each CTA holds its 128 rows x BLOCK_N columns), two stages, so
 //     the epilogue of tile i overlaps the MMAs of tile i+1.
-//   * Epilogue warps drain TMEM with tcgen05.ld, transpose 32 x 32 chunks through padded shared
+//   * Epilogue warps drain TMEM with tcgen05.ld, transpose 32 x 32 chunks through XOR-swizzled shared
 //     memory and read/write HBM with fully coalesced 128-bit accesses (4 rows x 128 B per warp
 //     instruction) while applying bias / quick_gelu / residual / position-embedding fusions.
 //
@@ -33,17 +33,19 @@ namespace mcm {
 constexpr int kGemm2Threads = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int kGemm2EpiWarps = 8;    // two per TMEM lane quadrant (= per SM sub-partition): one column half each
 constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
-constexpr int kStgLd = 36;           // staging row stride in floats (32 + 4: conflict-free 16-byte rows)
+constexpr int kStgLd = 32;           // staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
 
 template <int BLOCK_N>
 struct Gemm2Smem {
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 5 : 7;
+    static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
     static constexpr int kStagingBytes = kGemm2EpiWarps * 32 * kStgLd * 4;
-    static constexpr int kBarrierBytes = 1024;
+    static constexpr int kBarrierBytes = 256;
     static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /* alignment slack */;
+    static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+    static_assert((2 * kStages + 4) * 8 + 4 <= kBarrierBytes, "barrier area too small");
 };
 
 // ---- cluster / 2-CTA PTX ----
@@ -103,7 +105,7 @@ __device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar) {
         : "memory");
 }
 
-// One 32-row x 32-column chunk of the accumulator leaves through a padded smem transpose so that
+// One 32-row x 32-column chunk of the accumulator leaves through a swizzled smem transpose so that
 // global accesses are 4 rows x 128 B (fp32) or 4 rows x 64 B (fp16) per warp instruction.
 // All global reads of the chunk (residual rows / position rows) are issued BEFORE the TMEM load and
 // the transpose so their latency overlaps them.  t_addr: TMEM address (lane quadrant + column) of the
@@ -136,15 +138,15 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float*
     tmem_ld_wait();
     float4* w = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        w[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
-                           __uint_as_float(acc[4 * j + 3]));
+    for (int j = 0; j < 8; ++j)   // row `lane`, 16-byte chunk j -> slot j ^ (lane & 7): conflict-free both ways
+        w[j ^ (lane & 7)] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                        __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + 4 * i;
         const int m = m_base + r;
-        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgLd + 4 * cq);
+        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgLd + 4 * (cq ^ (r & 7)));
         if (m < p.m_valid) {
             if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16) {
                 v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;

@@ -86,7 +86,7 @@ def test_image_features_match_oracle(engine_factory, cfg_name, b):
     assert cos >= 0.9995, cos
 
 
-@pytest.mark.parametrize("noise,fpr_tol", [(0.8, 2.5e-3), (0.5, 2.5e-3)])
+@pytest.mark.parametrize("noise,fpr_tol", [(0.8, 2.5e-3), (0.68, 2.5e-3)])
 def test_fullsize_stream_metrics(noise, fpr_tol):
     """BASELINE config 2 shape at full stream size: ViT-B/16, K = 100, 5 000 ID + 5 000 OOD images.
 
@@ -146,7 +146,7 @@ def test_fullsize_stream_metrics(noise, fpr_tol):
         report("fullsize", dict(n=n, K=K, noise=noise, max_abs_err=float(err), score_std=float(res["id"][1].std()),
                                 auroc=float(m_got[0]), auroc_ref=float(m_ref[0]), aupr=float(m_got[1]),
                                 aupr_ref=float(m_ref[1]), fpr=float(m_got[2]), fpr_ref=float(m_ref[2])))
-        assert 0.55 < m_ref[0] < 0.999, f"harness AUROC {m_ref[0]} is vacuous"
+        assert 0.55 < m_ref[0] < 0.9995, f"harness AUROC {m_ref[0]} is vacuous"
         assert err <= 1e-3
         assert abs(m_got[0] - m_ref[0]) <= 5e-4, (m_got, m_ref)      # 0.05 pt AUROC
         assert abs(m_got[2] - m_ref[2]) <= fpr_tol, (m_got, m_ref)
