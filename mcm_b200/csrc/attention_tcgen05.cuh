@@ -56,6 +56,11 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU op; flushes denormal results to zero
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -202,15 +207,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tcgen05_fence_after();
             float row_sum = 1.f;
             if (warp_valid) {
-                // ---- pass 1: row max over the S valid keys ----
+                // ---- pass 1: row max over the S valid keys (only the last chunk can hold padded keys) ----
                 float mx = -INFINITY;
                 for (int ch = 0; ch < nfull; ++ch) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_s + ch * 32, v);
                     tmem_ld_wait();
+                    if (ch * 32 + 32 <= p.S) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (ch * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
+                        for (int e = 0; e < 32; e += 2)
+                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (ch * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
+                    }
                 }
                 if (rem16) {
                     uint32_t v[16];
@@ -221,20 +232,32 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         if (nfull * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
                 }
                 const float mc = mx * c;
-                // ---- pass 2: p = exp2(s * c - max * c); P (fp16) overwrites the first half of the S columns ----
-                float sum = 0.f;
+                // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns ----
+                float sum0 = 0.f, sum1 = 0.f;
                 for (int ch = 0; ch < nfull; ++ch) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_s + ch * 32, v);
                     tmem_ld_wait();
                     uint32_t pk[16];
+                    if (ch * 32 + 32 <= p.S) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int k0 = ch * 32 + 2 * e;
-                        const float p0 = (k0 < p.S) ? exp2f(__uint_as_float(v[2 * e]) * c - mc) : 0.f;
-                        const float p1 = (k0 + 1 < p.S) ? exp2f(__uint_as_float(v[2 * e + 1]) * c - mc) : 0.f;
-                        sum += p0 + p1;
-                        pk[e] = pack_op16x2(p0, p1);
+                        for (int e = 0; e < 16; ++e) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc));
+                            sum0 += p0;
+                            sum1 += p1;
+                            pk[e] = pack_op16x2(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int k0 = ch * 32 + 2 * e;
+                            const float p0 = (k0 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
+                            const float p1 = (k0 + 1 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
+                            sum0 += p0;
+                            sum1 += p1;
+                            pk[e] = pack_op16x2(p0, p1);
+                        }
                     }
                     tmem_st_32x32b_x16(t_s + ch * 16, pk);
                 }
@@ -246,15 +269,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int k0 = nfull * 32 + 2 * e;
-                        const float p0 = (k0 < p.S) ? exp2f(__uint_as_float(v[2 * e]) * c - mc) : 0.f;
-                        const float p1 = (k0 + 1 < p.S) ? exp2f(__uint_as_float(v[2 * e + 1]) * c - mc) : 0.f;
-                        sum += p0 + p1;
+                        const float p0 = (k0 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
+                        const float p1 = (k0 + 1 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
+                        sum0 += p0;
+                        sum1 += p1;
                         pk[e] = pack_op16x2(p0, p1);
                     }
                     tmem_st_32x32b_x8(t_s + nfull * 16, pk);
                 }
                 tmem_st_wait();
-                row_sum = sum;
+                row_sum = sum0 + sum1;
             }
             tcgen05_fence_before();
             __syncwarp();
