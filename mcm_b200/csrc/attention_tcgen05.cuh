@@ -189,7 +189,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const int quad = warp & 3;           // TMEM lane quadrant
         const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
         const uint32_t t_s = tmem_base + t_lane + g * 256;
-        uint8_t* stg = s_stage + (warp - 2) * 32 * 128;
+        const uint32_t stg = smem_u32(s_stage + (warp - 2) * 32 * 128);   // shared-space address of this warp's staging tile
         const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
         const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
         const int nfull = p.keys_pad >> 5;
@@ -302,7 +302,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         w.z = pack_op16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
                         w.w = pack_op16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
                         const int chunk = hc * 4 + q;
-                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = w;
+                        sts_v4u(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4), w);
                     }
                 }
             }
@@ -316,7 +316,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     const int r = (lane >> 3) + 4 * i;
                     const int row = wrow0 + r;
                     if (row < p.S) {
-                        const uint4 w = *reinterpret_cast<const uint4*>(stg + r * 128 + ((cq ^ (r & 7)) << 4));
+                        const uint4 w = lds_v4u(stg + r * 128 + ((cq ^ (r & 7)) << 4));
                         *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(img) * p.S + row) * D + h * 64 + cq * 8) = w;
                     }
                 }

@@ -111,7 +111,7 @@ __device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar) {
 // the transpose so their latency overlaps them.  t_addr: TMEM address (lane quadrant + column) of the
 // chunk; m_base: global row of this warp's first row; col0: first global column of the chunk.
 template <int EPI>
-__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float* stg, uint32_t t_addr, int m_base, int col0,
+__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32_t stg, uint32_t t_addr, int m_base, int col0,
                                                      int lane, const float4 bias) {
     const int cq = lane & 7;       // this lane's 4-column group
     const int r0 = lane >> 3;      // rows r0, r0 + 4, ..., r0 + 28
@@ -136,17 +136,17 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float*
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_addr, acc);
     tmem_ld_wait();
-    float4* w = reinterpret_cast<float4*>(stg + lane * kStgLd);
+    const uint32_t srow = stg + lane * (kStgLd * 4);
 #pragma unroll
     for (int j = 0; j < 8; ++j)   // row `lane`, 16-byte chunk j -> slot j ^ (lane & 7): conflict-free both ways
-        w[j ^ (lane & 7)] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                                        __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+        sts_v4(srow + ((j ^ (lane & 7)) << 4), make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                                           __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])));
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + 4 * i;
         const int m = m_base + r;
-        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgLd + 4 * (cq ^ (r & 7)));
+        float4 v = lds_v4(stg + r * (kStgLd * 4) + ((cq ^ (r & 7)) << 4));
         if (m < p.m_valid) {
             if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16) {
                 v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
@@ -167,6 +167,56 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, float*
                 *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow[i] * p.ldo + col) = v;
             }
         }
+    }
+    __syncwarp();
+}
+
+// fp16-output epilogues (bias, bias + quick_gelu): the math runs on the TMEM registers (row per
+// thread, 32 independent columns -> deep MUFU pipelining), only the packed fp16 result (64 B per
+// row) goes through the staging transpose, and HBM sees 8 rows x 64 B per warp instruction.
+template <int EPI>
+__device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, uint32_t stg, uint32_t t_addr, int m_base,
+                                                         int col0, int lane) {
+    static_assert(EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16, "fp16-output epilogues only");
+    uint32_t acc[32];
+    tmem_ld_32x32b_x32(t_addr, acc);
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform addresses: broadcast loads
+    float4 bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v0 = __uint_as_float(acc[4 * j + 0]) + bias[j].x;
+        float v1 = __uint_as_float(acc[4 * j + 1]) + bias[j].y;
+        float v2 = __uint_as_float(acc[4 * j + 2]) + bias[j].z;
+        float v3 = __uint_as_float(acc[4 * j + 3]) + bias[j].w;
+        if constexpr (EPI == EPI_BIAS_QGELU_F16) {
+            v0 = __fdividef(v0, 1.0f + __expf(-1.702f * v0));
+            v1 = __fdividef(v1, 1.0f + __expf(-1.702f * v1));
+            v2 = __fdividef(v2, 1.0f + __expf(-1.702f * v2));
+            v3 = __fdividef(v3, 1.0f + __expf(-1.702f * v3));
+        }
+        pk[2 * j + 0] = pack_op16x2(v0, v1);
+        pk[2 * j + 1] = pack_op16x2(v2, v3);
+    }
+    // staging tile: 32 rows x 64 B; 16-byte slot s of row r lives at slot s ^ ((r >> 1) & 3)  (conflict-free both ways)
+    const uint32_t srow = stg + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+        sts_v4u(srow + ((s4 ^ sw) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
+    __syncwarp();
+    const int slot = lane & 3;     // this lane's 8-column group
+    const int r0 = lane >> 2;      // rows r0, r0 + 8, r0 + 16, r0 + 24
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 8 * i;
+        const int m = m_base + r;
+        const uint4 v = lds_v4u(stg + r * 64 + ((slot ^ ((r >> 1) & 3)) << 4));
+        if (m < p.m_valid)
+            *reinterpret_cast<uint4*>(static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col0 + slot * 8) = v;
     }
     __syncwarp();
 }
@@ -273,7 +323,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
         const int half = ew >> 2;           // which half of the tile's columns this warp drains
         constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
-        float* stg = staging + ew * 32 * kStgLd;
+        const uint32_t stg = smem_u32(staging + ew * 32 * kStgLd);   // shared-space address of this warp's staging tile
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -285,7 +335,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 bias[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (EPI != EPI_POS_F32)
+                if constexpr (EPI == EPI_BIAS_RESID_F32)
                     bias[c] = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + c * 32 + 4 * (lane & 7)));
             }
             mbar_wait(&tmem_full[as], aphase);
@@ -293,8 +343,12 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
             if (m_base < p.m_valid) {
 #pragma unroll
-                for (int c = 0; c < kChunks; ++c)
-                    gemm2_epilogue_chunk<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias[c]);
+                for (int c = 0; c < kChunks; ++c) {
+                    if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16)
+                        gemm2_epilogue_chunk_f16<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane);
+                    else
+                        gemm2_epilogue_chunk<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias[c]);
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
