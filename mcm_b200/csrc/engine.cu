@@ -66,6 +66,7 @@ struct McmHandle {
     int G = 0, Np = 0, S = 0, D = 0, H = 0, F = 0, P = 0, L = 0, Kp = 0, Kpatch = 0;
     int num_sms = 0;
     bool gemm_1cta = false;  // debug A/B switch (env MCM_GEMM_1CTA=1): single-CTA 128 x BLOCK_N tiles instead of CTA pairs
+    int gemm_pairs = 1;      // CTA pairs per cluster (env MCM_GEMM_PAIRS=2: 4-CTA clusters with W-tile multicast)
     int64_t m_pad = 0, mp_pad = 0;  // padded token rows / patch rows for max_batch
     std::string err;
 
@@ -198,18 +199,35 @@ int launch_gemm_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, co
     return MCM_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int PAIRS>
 int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    static bool attr_done = false;
-    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI>;
-    if (!attr_done) {
+    static int max_clusters = 0;   // co-resident clusters of this instantiation (persistent grid size)
+    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI, PAIRS>;
+    constexpr int kCluster = 2 * PAIRS;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kGemm2Threads);
+    cfg.dynamicSmemBytes = Gemm2Smem<BN>::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters == 0) {
         MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
-        attr_done = true;
+        // clusters of 4 do not tile every GPC: ask the driver how many can be resident at once
+        cfg.gridDim = dim3(kCluster * (h->num_sms / kCluster));
+        int n = 0;
+        MCM_CUDA(h, cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        if (n <= 0) return fail(h, MCM_ECUDA, "no %d-CTA cluster of the GEMM kernel fits on this device", kCluster);
+        max_clusters = std::min(n, h->num_sms / kCluster);
     }
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int clusters = std::min(tiles, h->num_sms / 2);
-    kern<<<2 * clusters, kGemm2Threads, Gemm2Smem<BN>::kTotal, st>>>(ta, tb, p);
-    MCM_CUDA(h, cudaGetLastError());
+    const int tiles = ((p.m_tiles + PAIRS - 1) / PAIRS) * p.n_tiles;
+    const int clusters = std::min(tiles, max_clusters);
+    cfg.gridDim = dim3(kCluster * clusters);
+    MCM_CUDA(h, cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
     h->launches++;
     return MCM_OK;
 }
@@ -237,7 +255,9 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     if (!h->gemm_1cta) p.m_tiles = (M + kGemm2TileM - 1) / kGemm2TileM;
 #define MCM_GEMM_CASE(BN, E)                                                     \
     if (bn == BN && epi == E)                                                    \
-        return h->gemm_1cta ? launch_gemm_t<BN, E>(h, ta, tb, p, st) : launch_gemm2_t<BN, E>(h, ta, tb, p, st);
+        return h->gemm_1cta ? launch_gemm_t<BN, E>(h, ta, tb, p, st)                                         \
+               : h->gemm_pairs == 2 ? launch_gemm2_t<BN, E, 2>(h, ta, tb, p, st)                             \
+                                    : launch_gemm2_t<BN, E, 1>(h, ta, tb, p, st);
     MCM_GEMM_CASE(256, EPI_BIAS_F16)
     MCM_GEMM_CASE(256, EPI_BIAS_QGELU_F16)
     MCM_GEMM_CASE(256, EPI_BIAS_RESID_F32)
@@ -579,6 +599,8 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     {
         const char* e = getenv("MCM_GEMM_1CTA");
         h->gemm_1cta = e && e[0] == '1';
+        const char* e2 = getenv("MCM_GEMM_PAIRS");
+        h->gemm_pairs = (e2 && e2[0] == '2') ? 2 : 1;
     }
     const int D = h->D, F = h->F;
 
@@ -614,14 +636,14 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         MCM_TRY(dev_alloc(h, &w.ln1b, D, false));
         MCM_TRY(dev_alloc(h, &w.ln2g, D, false));
         MCM_TRY(dev_alloc(h, &w.ln2b, D, false));
-        const uint32_t wdiv = h->gemm_1cta ? 1 : 2;   // CTA pairs load half of the W tile each
+        const uint32_t wdiv = h->gemm_1cta ? 1 : 2 * h->gemm_pairs;   // each CTA of a cluster loads 1/2 or 1/4 of the W tile
         const uint32_t bnD = gemm_block_n(D) / wdiv, bn3D = gemm_block_n(3 * D) / wdiv, bnF = gemm_block_n(F) / wdiv;
         MCM_TRY(make_tmap(h, &w.tm_wqkv, w.wqkv, 3 * D, D, bn3D));
         MCM_TRY(make_tmap(h, &w.tm_wo, w.wo, D, D, bnD));
         MCM_TRY(make_tmap(h, &w.tm_w1, w.w1, F, D, bnF));
         MCM_TRY(make_tmap(h, &w.tm_w2, w.w2, D, F, bnD));
     }
-    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D) / (h->gemm_1cta ? 1 : 2)));
+    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D) / (h->gemm_1cta ? 1 : 2 * h->gemm_pairs)));
     h->loaded.assign(SLOT_GLOBALS + 16 * h->L, 0);
     h->stage_elems = (size_t)std::max(std::max((size_t)F * D, (size_t)D * h->Kpatch), std::max((size_t)h->S * D, (size_t)h->P * D));
     MCM_TRY(dev_alloc(h, &h->stage, h->stage_elems, false));
@@ -861,7 +883,7 @@ int mcm_dbg_gemm(McmHandle* h, const void* a, const void* w, const float* bias, 
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
-    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / (h->gemm_1cta ? 1 : 2)))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / (h->gemm_1cta ? 1 : 2 * h->gemm_pairs)))) return rc;
     return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, epi, bias, out, resid, nullptr, 0, 0, static_cast<cudaStream_t>(stream));
 }
 

@@ -76,6 +76,18 @@ __device__ __forceinline__ void tma_load_2d_cta2(void* smem_dst, const void* tma
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same, multicast: the box lands at the same smem offset in every CTA of `cta_mask`; the byte count is
+// signalled, per destination CTA, on the barrier at `bar`'s offset in that CTA's PAIR LEADER (the
+// barrier address carries an even CTA rank) -- the form CUTLASS' SM100_TMA_2SM_LOAD_MULTICAST uses.
+__device__ __forceinline__ void tma_load_2d_cta2_mc(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int32_t c0,
+                                                    int32_t c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+        : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cta2(uint32_t* dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols)
@@ -97,11 +109,11 @@ __device__ __forceinline__ void umma_f16_cta2(uint32_t tmem_d, uint64_t desc_a, 
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrive (once all previously issued MMAs retired) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar) {
+// arrive (once all previously issued MMAs retired) on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar, uint16_t cta_mask) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
         : "memory");
 }
 
@@ -221,9 +233,13 @@ __device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, ui
     __syncwarp();
 }
 
-// p.m_tiles here counts 256-row cluster tiles.
-template <int BLOCK_N, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+// p.m_tiles counts 256-row pair tiles.  PAIRS = 1: cluster of 2 CTAs (one pair).  PAIRS = 2: cluster of
+// 4 CTAs = two pairs working on vertically adjacent 256-row tiles of the SAME n-block; every CTA
+// fetches only a QUARTER of the W tile and multicasts it to its twin in the other pair, which cuts the
+// L2 -> SM operand traffic (the measured limiter of the k-loop) from 64 KB to 48 KB per pair k-block.
+// Launched with cudaLaunchKernelEx + cluster dimension 2 * PAIRS.
+template <int BLOCK_N, int EPI, int PAIRS>
+__global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const GemmParams p) {
     using L = Gemm2Smem<BLOCK_N>;
@@ -243,17 +259,24 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1;
-    const int num_clusters = gridDim.x >> 1;
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    static_assert(PAIRS == 1 || PAIRS == 2, "PAIRS");
+    const uint32_t crank = cluster_ctarank();          // 0 .. 2 * PAIRS - 1
+    const uint32_t rank = crank & 1;                   // rank inside the CTA pair (0 = leader)
+    const uint32_t pair = crank >> 1;
+    const uint32_t leader = crank & ~1u;               // cluster rank of this pair's leader
+    const int cluster_id = blockIdx.x / (2 * PAIRS);
+    const int num_clusters = gridDim.x / (2 * PAIRS);
+    const int m_ctiles = (p.m_tiles + PAIRS - 1) / PAIRS;      // cluster tiles along M
+    const int num_tiles = m_ctiles * p.n_tiles;
+    constexpr uint16_t kAllMask = (1u << (2 * PAIRS)) - 1;
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], PAIRS);   // every pair that reads this stage (all write into it) must release it
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -269,29 +292,35 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     if (warp == 0) {
         if (elect_one()) {
-            // ===== TMA producer (both CTAs): own A rows, own half of W; bytes land on the leader's full barrier =====
+            // ===== TMA producer (every CTA): own A rows, own share of W; bytes land on the pair leader's full barrier =====
             int stage = 0;
             uint32_t phase = 0;
+            constexpr int kWRows = BLOCK_N / (2 * PAIRS);     // W rows this CTA fetches per k-block
+            const uint16_t w_mask = static_cast<uint16_t>((1u << rank) | (PAIRS == 2 ? (1u << (rank + 2)) : 0u));
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile / p.n_tiles;
-                const int n_blk = tile - m_blk * p.n_tiles;
+                const int mc = tile / p.n_tiles;
+                const int n_blk = tile - mc * p.n_tiles;
+                const int m_blk = mc * PAIRS + static_cast<int>(pair);
                 const int a_row = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM;
-                const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+                const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) + static_cast<int>(pair) * kWRows;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
-                    uint8_t* sb = sa + L::kABytes;
+                    uint8_t* sb = sa + L::kABytes + static_cast<int>(pair) * (kWRows * kGemmBlockK * 2);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-                    const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                    const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), leader);
                     tma_load_2d_cta2(sa, &tmap_a, bar, kb * kGemmBlockK, a_row);
-                    tma_load_2d_cta2(sb, &tmap_b, bar, kb * kGemmBlockK, b_row);
+                    if constexpr (PAIRS == 1)
+                        tma_load_2d_cta2(sb, &tmap_b, bar, kb * kGemmBlockK, b_row);
+                    else
+                        tma_load_2d_cta2_mc(sb, &tmap_b, bar, kb * kGemmBlockK, b_row, w_mask);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (rank == 0 && elect_one()) {
-            // ===== MMA issuer (leader CTA only) =====
+            // ===== MMA issuer (pair leaders only) =====
             constexpr uint32_t idesc = make_idesc_f16(kGemm2TileM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -310,10 +339,10 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 16; ++k)
                         umma_f16_cta2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_cta2_mc(&empty_bar[stage]);
+                    umma_commit_cta2_mc(&empty_bar[stage], kAllMask);   // the stage is written by CTAs of every pair
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_cta2_mc(&tmem_full[as]);
+                umma_commit_cta2_mc(&tmem_full[as], pair_mask);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -327,8 +356,9 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m_blk = tile / p.n_tiles;
-            const int n_blk = tile - m_blk * p.n_tiles;
+            const int mc = tile / p.n_tiles;
+            const int n_blk = tile - mc * p.n_tiles;
+            const int m_blk = mc * PAIRS + static_cast<int>(pair);
             const int m_base = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
             const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
             float4 bias[kChunks];
@@ -354,7 +384,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             __syncwarp();
             if (lane == 0) {
                 if (rank == 0) mbar_arrive(&tmem_empty[as]);
-                else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), leader));
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
