@@ -19,6 +19,8 @@ attention_cls_kernel(const op16_t* __restrict__ qkv, const float* __restrict__ x
                      float* __restrict__ x_cls, int b, int S, int H, float scale) {
     __shared__ float s_q[kClsWarps][64];
     __shared__ float s_p[kClsWarps][kClsMaxS];
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * kClsWarps + warp;
     if (item >= b * H) return;

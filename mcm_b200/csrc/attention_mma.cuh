@@ -25,6 +25,8 @@ attention_mma_kernel(const op16_t* __restrict__ qkv, op16_t* __restrict__ out, i
     op16_t* sK = reinterpret_cast<op16_t*>(attn_smem);
     op16_t* sV = sK + static_cast<size_t>(keys_pad) * kAttnLd;
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int h = blockIdx.x % H;
     const int img = blockIdx.x / H;
     const int ld = 3 * H * kAttnDh;

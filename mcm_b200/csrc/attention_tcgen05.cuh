@@ -75,6 +75,46 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
+// running max over one 32-key chunk of a score row (keys k0 .. k0 + 31; keys >= S are padding)
+__device__ __forceinline__ float atc_chunk_max(const uint32_t (&v)[32], int k0, int S, float mx) {
+    if (k0 + 32 <= S) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (k0 + e < S) mx = fmaxf(mx, __uint_as_float(v[e]));
+    }
+    return mx;
+}
+// p = 2^(s * c - mc) for one 32-key chunk, accumulated into two partial row sums and written to TMEM
+// as 16 packed fp16 pairs (the A operand of P.V) at `t_p`
+__device__ __forceinline__ void atc_chunk_exp(const uint32_t (&v)[32], int k0, int S, float c, float mc, float& sum0,
+                                              float& sum1, uint32_t t_p) {
+    uint32_t pk[16];
+    if (k0 + 32 <= S) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc));
+            sum0 += p0;
+            sum1 += p1;
+            pk[e] = pack_op16x2(p0, p1);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int k = k0 + 2 * e;
+            const float p0 = (k < S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
+            const float p1 = (k + 1 < S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
+            sum0 += p0;
+            sum1 += p1;
+            pk[e] = pack_op16x2(p0, p1);
+        }
+    }
+    tmem_st_32x32b_x16(t_p, pk);
+}
+
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                          const AtcParams p) {
@@ -112,11 +152,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();   // everything above overlapped the predecessor's tail; global data is touched only below
 
     if (warp == 0) {
         if (elect_one()) {
@@ -207,21 +249,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tcgen05_fence_after();
             float row_sum = 1.f;
             if (warp_valid) {
-                // ---- pass 1: row max over the S valid keys (only the last chunk can hold padded keys) ----
+                // ---- pass 1: row max over the S valid keys (only the last chunk can hold padded keys);
+                //      TMEM loads are issued two chunks at a time so their latencies overlap ----
                 float mx = -INFINITY;
-                for (int ch = 0; ch < nfull; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                for (int ch = 0; ch < nfull; ch += 2) {
+                    uint32_t va[32], vb[32];
+                    const bool two = ch + 1 < nfull;
+                    tmem_ld_32x32b_x32(t_s + ch * 32, va);
+                    if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
                     tmem_ld_wait();
-                    if (ch * 32 + 32 <= p.S) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2)
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (ch * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
-                    }
+                    mx = atc_chunk_max(va, ch * 32, p.S, mx);
+                    if (two) mx = atc_chunk_max(vb, ch * 32 + 32, p.S, mx);
                 }
                 if (rem16) {
                     uint32_t v[16];
@@ -232,34 +270,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         if (nfull * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
                 }
                 const float mc = mx * c;
-                // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns ----
+                // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns.
+                //      Software-pipelined: the TMEM load of chunk i + 1 is in flight while chunk i is in the MUFU ----
                 float sum0 = 0.f, sum1 = 0.f;
-                for (int ch = 0; ch < nfull; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-                    if (ch * 32 + 32 <= p.S) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc));
-                            sum0 += p0;
-                            sum1 += p1;
-                            pk[e] = pack_op16x2(p0, p1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int k0 = ch * 32 + 2 * e;
-                            const float p0 = (k0 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
-                            const float p1 = (k0 + 1 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
-                            sum0 += p0;
-                            sum1 += p1;
-                            pk[e] = pack_op16x2(p0, p1);
+                {
+                    uint32_t va[32], vb[32];
+                    if (nfull > 0) tmem_ld_32x32b_x32(t_s, va);
+                    for (int ch = 0; ch < nfull; ch += 2) {
+                        tmem_ld_wait();
+                        const bool two = ch + 1 < nfull;
+                        if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
+                        atc_chunk_exp(va, ch * 32, p.S, c, mc, sum0, sum1, t_s + ch * 16);
+                        if (two) {
+                            tmem_ld_wait();
+                            if (ch + 2 < nfull) tmem_ld_32x32b_x32(t_s + ch * 32 + 64, va);
+                            atc_chunk_exp(vb, ch * 32 + 32, p.S, c, mc, sum0, sum1, t_s + ch * 16 + 16);
                         }
                     }
-                    tmem_st_32x32b_x16(t_s + ch * 16, pk);
                 }
                 if (rem16) {
                     uint32_t v[16];

@@ -181,6 +181,36 @@ int make_tmap(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uin
     return MCM_OK;
 }
 
+// Launch with programmatic dependent launch (every kernel of the forward chain calls pdl_wait()) and an
+// optional thread-block cluster.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+inline int cuda_rc(McmHandle* h, cudaError_t e) {
+    return e == cudaSuccess ? MCM_OK : fail(h, MCM_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
 inline int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
 template <int BN, int EPI>
@@ -193,8 +223,7 @@ int launch_gemm_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, co
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, p);
-    MCM_CUDA(h, cudaGetLastError());
+    MCM_CUDA(h, launch_k(kern, dim3(grid), dim3(kGemmThreads), GemmSmem<BN>::kTotal, st, 1, ta, tb, p));
     h->launches++;
     return MCM_OK;
 }
@@ -226,8 +255,7 @@ int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, c
     }
     const int tiles = ((p.m_tiles + PAIRS - 1) / PAIRS) * p.n_tiles;
     const int clusters = std::min(tiles, max_clusters);
-    cfg.gridDim = dim3(kCluster * clusters);
-    MCM_CUDA(h, cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    MCM_CUDA(h, launch_k(kern, dim3(kCluster * clusters), dim3(kGemm2Threads), Gemm2Smem<BN>::kTotal, st, kCluster, ta, tb, p));
     h->launches++;
     return MCM_OK;
 }
@@ -294,10 +322,8 @@ int launch_layernorm(McmHandle* h, const float* x, const float* g, const float* 
     int rc = dispatch_vec(h, D, [&](auto vec) {
         constexpr int V = decltype(vec)::value;
         if (out_f16)
-            layernorm_kernel<V, true><<<grid, kRowThreads, 0, st>>>(x, g, b, out, M, eps);
-        else
-            layernorm_kernel<V, false><<<grid, kRowThreads, 0, st>>>(x, g, b, out, M, eps);
-        return MCM_OK;
+            return cuda_rc(h, launch_k(layernorm_kernel<V, true>, dim3(grid), dim3(kRowThreads), 0, st, 1, x, g, b, out, M, eps));
+        return cuda_rc(h, launch_k(layernorm_kernel<V, false>, dim3(grid), dim3(kRowThreads), 0, st, 1, x, g, b, out, M, eps));
     });
     if (rc) return rc;
     MCM_CUDA(h, cudaGetLastError());
@@ -323,8 +349,7 @@ int launch_attention_mma(McmHandle* h, const op16_t* qkv, op16_t* out, int b, in
     if (nwarps < 1) nwarps = 1;
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    attention_mma_kernel<<<b * H, nwarps * 32, smem, st>>>(qkv, out, S, H, keys_pad, scale_log2e);
-    MCM_CUDA(h, cudaGetLastError());
+    MCM_CUDA(h, launch_k(attention_mma_kernel, dim3(b * H), dim3(nwarps * 32), smem, st, 1, qkv, out, S, H, keys_pad, scale_log2e));
     h->launches++;
     return MCM_OK;
 }
@@ -351,8 +376,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     const int items = b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    attention_tcgen05_kernel<<<grid, kAtcThreads, smem, st>>>(tq, tkv, p);
-    MCM_CUDA(h, cudaGetLastError());
+    MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, p));
     h->launches++;
     return MCM_OK;
 }
@@ -361,15 +385,16 @@ int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T,
                 cudaStream_t st) {
     if (b <= 0) return MCM_OK;
     ProfScope prof(h, MCM_PROF_TAIL, st);
-    pooled_layernorm_kernel<<<(b + 7) / 8, 256, 0, st>>>(x, row_stride, h->D, b, h->post_g, h->post_b, h->cfg.eps, h->t_ln);
+    MCM_CUDA(h, launch_k(pooled_layernorm_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, x, row_stride, h->D, b, h->post_g,
+                         h->post_b, h->cfg.eps, h->t_ln));
     float* f = feats ? feats : h->t_feat;
     dim3 g1((h->P + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
-    sgemm_tn_kernel<<<g1, 256, 0, st>>>(h->t_ln, h->wproj, f, b, h->P, h->D);
+    MCM_CUDA(h, launch_k(sgemm_tn_kernel, g1, dim3(256), 0, st, 1, h->t_ln, h->wproj, f, b, h->P, h->D));
     h->launches += 2;
     if (scores) {
         dim3 g2((h->K + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
-        sgemm_tn_kernel<<<g2, 256, 0, st>>>(f, h->bank, h->t_logit, b, h->K, h->P);
-        score_rows_kernel<<<(b + 7) / 8, 256, 0, st>>>(f, h->t_logit, h->P, h->K, b, T, kind, scores);
+        MCM_CUDA(h, launch_k(sgemm_tn_kernel, g2, dim3(256), 0, st, 1, f, h->bank, h->t_logit, b, h->K, h->P));
+        MCM_CUDA(h, launch_k(score_rows_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, f, h->t_logit, h->P, h->K, b, T, kind, scores));
         h->launches += 2;
     }
     MCM_CUDA(h, cudaGetLastError());
@@ -379,9 +404,8 @@ int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T,
 int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
     {
         ProfScope prof(h, MCM_PROF_PATCHIFY, st);
-        patchify_kernel<<<b * h->G, 256, 0, st>>>(images, h->patches, h->G, h->cfg.patch, h->Kp);
+        MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), 0, st, 1, images, h->patches, h->G, h->cfg.patch, h->Kp));
     }
-    MCM_CUDA(h, cudaGetLastError());
     h->launches++;
     int rc = launch_gemm(h, MCM_PROF_GEMM_PATCH, h->tm_patches, h->tm_wpatch, b * h->Np, h->D, h->Kp, EPI_POS_F32, nullptr, h->x, nullptr,
                          h->pos, h->Np, h->S, st);
@@ -392,9 +416,8 @@ int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
     ProfScope prof(h, MCM_PROF_EMBED_FINISH, st);
     rc = dispatch_vec(h, h->D, [&](auto vec) {
         constexpr int V = decltype(vec)::value;
-        embed_finish_kernel<V><<<grid, kRowThreads, 0, st>>>(h->x, h->xn, h->cls, h->pos, h->pre_g, h->pre_b, l0.ln1g,
-                                                              l0.ln1b, M, h->S, h->cfg.eps);
-        return MCM_OK;
+        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xn, h->cls, h->pos,
+                                   h->pre_g, h->pre_b, l0.ln1g, l0.ln1b, M, h->S, h->cfg.eps));
     });
     if (rc) return rc;
     MCM_CUDA(h, cudaGetLastError());
@@ -418,10 +441,9 @@ int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st, con
             // only query row 0 of every image is consumed after this point (HF:685)
             {
                 ProfScope prof(h, MCM_PROF_ATTENTION, st);
-                attention_cls_kernel<<<(b * h->H + kClsWarps - 1) / kClsWarps, kClsWarps * 32, 0, st>>>(
-                    h->qkv, h->x, h->attn, h->x_cls, b, h->S, h->H, 0.125f);
+                MCM_CUDA(h, launch_k(attention_cls_kernel, dim3((b * h->H + kClsWarps - 1) / kClsWarps), dim3(kClsWarps * 32), 0,
+                                     st, 1, h->qkv, h->x, h->attn, h->x_cls, b, h->S, h->H, 0.125f));
             }
-            MCM_CUDA(h, cudaGetLastError());
             h->launches++;
             if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st))) return rc;
             if ((rc = launch_layernorm(h, h->x_cls, w.ln2g, w.ln2b, h->xn, b, D, h->cfg.eps, true, st))) return rc;

@@ -154,11 +154,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         if (elect_one()) {

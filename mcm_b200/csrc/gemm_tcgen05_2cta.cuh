@@ -284,11 +284,13 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 1) tmem_alloc_cta2<kTmemCols>(tmem_ptr);
     tcgen05_fence_before();
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();   // everything above overlapped the predecessor's tail; global data is touched only below
 
     if (warp == 0) {
         if (elect_one()) {

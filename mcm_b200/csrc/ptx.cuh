@@ -229,6 +229,14 @@ __device__ __forceinline__ void mma_op16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// ------------------------------------------ programmatic dependent launch (PDL) ---
+// Every kernel of the forward chain is launched with programmaticStreamSerialization: it may become
+// resident (barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains, and
+// blocks in pdl_wait() until the predecessor grid has completed and flushed its memory.  Both are
+// no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // --------------------------------------------- explicit shared-space accesses ---
 // Pointers carved out of the dynamic shared buffer through integer alignment lose their address
 // space, and the compiler falls back to generic LD/ST (slower, scoreboarded like global loads).

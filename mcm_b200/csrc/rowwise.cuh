@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(kRowThreads)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  void* __restrict__ out, int M, float eps) {
     constexpr int D = 128 * VEC;
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -102,6 +104,8 @@ embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xn, const float*
                     const float* __restrict__ pos, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
                     const float* __restrict__ ln1_g, const float* __restrict__ ln1_b, int M, int S, float eps) {
     constexpr int D = 128 * VEC;
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -127,6 +131,8 @@ embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xn, const float*
 // reads are contiguous 224-float image rows, writes are p-element runs.
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int W = G * p;
     const int gy = blockIdx.x % G;
     const int b = blockIdx.x / G;

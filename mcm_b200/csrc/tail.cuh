@@ -20,6 +20,8 @@ enum ScoreKind : int { SCORE_MCM = 0, SCORE_MAX_LOGIT = 1, SCORE_ENERGY = 2, SCO
 __global__ void __launch_bounds__(256)
 pooled_layernorm_kernel(const float* __restrict__ x, size_t row_stride, int D, int b, const float* __restrict__ g,
                         const float* __restrict__ be, float eps, float* __restrict__ ln) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (img >= b) return;
@@ -47,6 +49,8 @@ __global__ void __launch_bounds__(256)
 sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int Kd) {
     __shared__ float sA[kSgemmK][kSgemmTile + 4];
     __shared__ float sB[kSgemmK][kSgemmTile + 4];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * kSgemmTile, n0 = blockIdx.x * kSgemmTile;
     const int lr = tid >> 2;         // 0..63: tile row this thread loads
@@ -95,6 +99,8 @@ sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
 __global__ void __launch_bounds__(256)
 score_rows_kernel(const float* __restrict__ feats, const float* __restrict__ logits, int P, int K, int b, float T,
                   int kind, float* __restrict__ scores) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (img >= b) return;
