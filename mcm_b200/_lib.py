@@ -61,7 +61,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library; ``MCM_B200_LIB`` selects an A/B variant built by ``build.build_variant``."""
+    return os.environ.get("MCM_B200_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

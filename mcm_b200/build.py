@@ -36,6 +36,19 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
+def build_variant(name: str, defines) -> str:
+    """A/B builds for GPU experiments: ``_C/libmcm_b200_<name>.so`` compiled with extra ``-D`` flags;
+    select it at run time with ``MCM_B200_LIB=<path>``."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(OUT_DIR, exist_ok=True)
+    out = os.path.join(OUT_DIR, f"libmcm_b200_{name}.so")
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out, os.path.join(CSRC, "engine.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/engine.cu`` (which includes every kernel header) into the shared library."""
     if not force and not is_stale():

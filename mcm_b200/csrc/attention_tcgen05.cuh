@@ -25,6 +25,10 @@
 #include <cuda.h>
 #include "ptx.cuh"
 
+#ifndef MCM_ATC_PIPE
+#define MCM_ATC_PIPE 0   // 1: software-pipeline the pass-2 TMEM loads (measured slower: more registers, no MUFU gain)
+#endif
+
 namespace mcm {
 
 constexpr int kAtcThreads = 320;
@@ -273,6 +277,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns.
                 //      Software-pipelined: the TMEM load of chunk i + 1 is in flight while chunk i is in the MUFU ----
                 float sum0 = 0.f, sum1 = 0.f;
+#if MCM_ATC_PIPE
                 {
                     uint32_t va[32], vb[32];
                     if (nfull > 0) tmem_ld_32x32b_x32(t_s, va);
@@ -288,6 +293,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         }
                     }
                 }
+#else
+                for (int ch = 0; ch < nfull; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                    tmem_ld_wait();
+                    atc_chunk_exp(v, ch * 32, p.S, c, mc, sum0, sum1, t_s + ch * 16);
+                }
+#endif
                 if (rem16) {
                     uint32_t v[16];
                     tmem_ld_32x32b_x16(t_s + nfull * 32, v);

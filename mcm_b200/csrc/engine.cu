@@ -192,9 +192,12 @@ cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int n = 0;
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
+    static const bool no_pdl = [] { const char* e = getenv("MCM_NO_PDL"); return e && e[0] == '1'; }();   // A/B switch
+    if (!no_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
     if (cluster > 1) {
         attr[n].id = cudaLaunchAttributeClusterDimension;
         attr[n].val.clusterDim.x = cluster;

@@ -66,7 +66,7 @@ def test_golden_scores_and_metrics(case, golden_dir):
         eng.close()
 
 
-@pytest.mark.parametrize("cfg_name,b", [("tiny", 9), ("small", 5), ("ViT-B/16", 4)])
+@pytest.mark.parametrize("cfg_name,b", [("tiny", 9), ("small", 5), ("ViT-B/16", 4), ("ViT-B/32", 3), ("ViT-L/14", 2)])
 def test_image_features_match_oracle(engine_factory, cfg_name, b):
     """Seam 2: net.get_image_features(pixel_values=) vs the fp32 oracle tower."""
     from mcm_b200 import synth

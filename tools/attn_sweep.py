@@ -1,0 +1,28 @@
+"""GPU-box timing of the attention kernel alone (ViT-B/16 shape): 20 launches, CUDA events."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mcm_b200 import synth  # noqa: E402
+from mcm_b200.engine import McmEngine  # noqa: E402
+
+cfg = synth.CFGS["tiny"]
+eng = McmEngine.from_state_dict(synth.synth_vision_state_dict(cfg, 5), cfg, max_batch=4)
+for b, S, H in [(256, 197, 12), (256, 50, 12), (64, 197, 12)]:
+    qkv = (torch.randn(b * S, 3 * H * 64, device="cuda") * 1.5).to(torch.float16)
+    for _ in range(3):
+        eng.dbg_attention(qkv, b, S, H)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        eng.dbg_attention(qkv, b, S, H)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / 20
+    print(json.dumps(dict(lib=os.environ.get("MCM_B200_LIB", "default"), mma=os.environ.get("MCM_ATTN_MMA", "0"), b=b, S=S, H=H,
+                          us=us, tflops=4.0 * b * H * S * S * 64 / us / 1e6)), flush=True)
