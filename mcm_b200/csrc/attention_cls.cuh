@@ -34,8 +34,7 @@ attention_cls_kernel(const op16_t* __restrict__ qkv, const float* __restrict__ x
         *reinterpret_cast<float2*>(x_cls + static_cast<size_t>(img) * D + h * 64 + lane * 2) = v;
     }
     {
-        const __half2 q2 = *reinterpret_cast<const __half2*>(base + lane * 2);
-        const float2 qf = __half22float2(q2);
+        const float2 qf = unpack_op16x2(*reinterpret_cast<const uint32_t*>(base + lane * 2));
         s_q[warp][lane * 2] = qf.x;
         s_q[warp][lane * 2 + 1] = qf.y;
     }
@@ -49,10 +48,10 @@ attention_cls_kernel(const op16_t* __restrict__ qkv, const float* __restrict__ x
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const uint4 u = __ldg(kr + c);
-            const __half2* hp = reinterpret_cast<const __half2*>(&u);
+            const uint32_t* hp = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float2 kf = __half22float2(hp[e]);
+                const float2 kf = unpack_op16x2(hp[e]);
                 acc = fmaf(kf.x, s_q[warp][c * 8 + e * 2], acc);
                 acc = fmaf(kf.y, s_q[warp][c * 8 + e * 2 + 1], acc);
             }
@@ -75,7 +74,7 @@ attention_cls_kernel(const op16_t* __restrict__ qkv, const float* __restrict__ x
     float o0 = 0.f, o1 = 0.f;
     const op16_t* vbase = base + 2 * D + lane * 2;
     for (int j = 0; j < S; ++j) {
-        const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(j) * ld));
+        const float2 vf = unpack_op16x2(*reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j) * ld));
         const float p = s_p[warp][j];
         o0 = fmaf(p, vf.x, o0);
         o1 = fmaf(p, vf.y, o1);

@@ -13,9 +13,18 @@ namespace mcm {
 // the AUROC / FPR95 parity with the fp32 reference is sensitive to -- and CLIP's activations and
 // weights sit comfortably inside fp16 range (OpenAI released and runs CLIP in fp16).  Accumulation,
 // the residual stream, LayerNorm, softmax and the scoring tail stay fp32.
+#ifdef MCM_OP_BF16   // A/B build only (tools/): bf16 operands, to measure the precision / power trade-off
+}  // namespace mcm
+#include <cuda_bf16.h>
+namespace mcm {
+using op16_t = __nv_bfloat16;
+constexpr uint32_t kUmmaFmt16 = 1;
+__device__ __forceinline__ op16_t to_op16(float v) { return __float2bfloat16_rn(v); }
+#else
 using op16_t = __half;
 constexpr uint32_t kUmmaFmt16 = 0;  // tcgen05 kind::f16 operand format: 0 = F16, 1 = BF16
 __device__ __forceinline__ op16_t to_op16(float v) { return __float2half_rn(v); }
+#endif
 
 #ifndef MCM_WAIT_TIMEOUT_CYCLES
 // mbarrier waits trap instead of hanging the GPU if a pipeline deadlocks (about two seconds of
@@ -224,7 +233,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t sad
 // D(16x8,f32) += A(16x16,fp16,row) * B(16x8,fp16,col)
 __device__ __forceinline__ void mma_op16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
+#ifdef MCM_OP_BF16
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#else
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#endif
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -236,6 +249,15 @@ __device__ __forceinline__ void mma_op16_16816(float (&d)[4], const uint32_t (&a
 // no-ops for a launch without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// two packed 16-bit operands -> fp32 pair
+__device__ __forceinline__ float2 unpack_op16x2(uint32_t w) {
+#ifdef MCM_OP_BF16
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+#else
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+#endif
+}
 
 // --------------------------------------------- explicit shared-space accesses ---
 // Pointers carved out of the dynamic shared buffer through integer alignment lose their address
@@ -259,7 +281,11 @@ __device__ __forceinline__ uint4 lds_v4u(uint32_t saddr) {
 
 // ------------------------------------------------------------------- misc ---
 __device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi) {
+#ifdef MCM_OP_BF16
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+#else
     __half2 v = __floats2half2_rn(lo, hi);
+#endif
     return *reinterpret_cast<uint32_t*>(&v);
 }
 

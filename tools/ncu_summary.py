@@ -59,5 +59,24 @@ def full(path):
                 print(f"  {h.split('TriageCompute.')[-1]:92s} {units[i]:16s} {row[i]}")
 
 
+def traffic(path):
+    """JSON {kernel name: {"dram_bytes_per_launch": read + write, "launches_captured": n}} for bench.py's
+    roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(out.splitlines()))
+    hdr, units = r[0], r[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    agg = {}
+    for row in r[2:]:
+        name = re.sub(r"\(.*", "", row[ik]).replace("void ", "")
+        b = float(row[ir].replace(",", "")) * scale[units[ir]] + float(row[iw].replace(",", "")) * scale[units[iw]]
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += b
+        a[1] += 1
+    print(json.dumps({k: {"dram_bytes_per_launch": v[0] / v[1], "launches_captured": v[1]} for k, v in agg.items()}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
