@@ -12,6 +12,7 @@ done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 60 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-1800
 if [ "$1" != "noncu" ]; then
+timeout 600 python tools/attn_sweep.py > gpurun_out/attn_sweep.log 2>&1
 timeout 600 python tools/gemm_sweep.py > gpurun_out/gemm_sweep.log 2>&1; echo "sweep exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python tools/ncu_step.py --steps 1 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_f16 -s 14 -c 4 -f -o gpurun_out/prof_gemm python tools/ncu_step.py --steps 1 > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm exit $?"
