@@ -241,6 +241,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const int nfull = p.keys_pad >> 5;
         const bool rem16 = (p.keys_pad & 16) != 0;
         const float c = p.scale_log2e;
+        // Stagger the two groups by half a period: group 1 starts its first softmax only when group 0 has
+        // finished its first one, so from then on one group is in the MUFU-bound softmax while the tensor
+        // core serves the other group's P.V / next QK^T (the MMA warp issues in exactly that order).
+#ifndef MCM_ATC_NO_STAGGER
+        if (g == 1 && n_units > 1) mbar_wait(&p_full[0], 0);
+#endif
         for (uint32_t u = g; u < n_units; u += 2) {
             const uint32_t j = u >> 1;
             const uint32_t iu = u / upi;

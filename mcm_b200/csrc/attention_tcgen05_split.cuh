@@ -156,6 +156,12 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const
         float* x_sum = s_xch + 512 + (g * 2) * 128;
         const int blk_lo = hf ? nb0 : 0, blk_hi = hf ? nb : nb0;
         const float c = p.scale_log2e;
+        // Stagger the two groups by half a period: group 1 starts its first softmax only when group 0 has
+        // finished its first one, so from then on one group is in the MUFU-bound softmax while the tensor
+        // core serves the other group's P.V / next QK^T (the MMA warp issues in exactly that order).
+#ifndef MCM_ATC_NO_STAGGER
+        if (g == 1 && n_units > 1) mbar_wait(&p_full[0], 0);
+#endif
         for (uint32_t u = g; u < n_units; u += 2) {
             const uint32_t j = u >> 1;
             const uint32_t iu = u / upi;
