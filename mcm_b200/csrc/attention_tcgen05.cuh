@@ -41,7 +41,18 @@ struct AtcParams {
     int units_per_item;      // ceil(S / 128)
     float scale_log2e;       // dh^-0.5 * log2(e)
     op16_t* out;
+    long long* trace;        // debug builds (-DMCM_ATC_TRACE): per-phase clock64 stamps of CTA 0, else unused
 };
+
+#ifdef MCM_ATC_TRACE
+// trace[role][unit][event]: role 0 = MMA thread, 1 = softmax warp of group 0, 2 = softmax warp of group 1
+#define ATC_TRACE(role, unit, ev)                                                              \
+    do {                                                                                       \
+        if (p.trace && blockIdx.x == 0 && (unit) < 16) p.trace[((role) * 16 + (unit)) * 8 + (ev)] = clock64(); \
+    } while (0)
+#else
+#define ATC_TRACE(role, unit, ev) do {} while (0)
+#endif
 
 __host__ __device__ inline int atc_smem_bytes(int keys_pad) {
     return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
@@ -206,6 +217,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 for (int k = 0; k < 4; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
                 umma_commit(&q_empty[qs]);
                 umma_commit(&s_full[buf]);
+                ATC_TRACE(0, v, 0);                       // QK^T of unit v issued
             };
             if (n_units > 0) issue_qk(0);
             if (n_units > 1) issue_qk(1);
@@ -214,6 +226,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const uint32_t iu = u / upi;
                 const int kvs = iu & 1;
                 mbar_wait(&p_full[buf], (u >> 1) & 1);
+                ATC_TRACE(0, u, 1);                       // P of unit u ready
                 tcgen05_fence_after();
                 // V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
                 const uint64_t vdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes + kv_bytes), 1024, 1024);
@@ -221,9 +234,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const uint32_t a = tmem_base + buf * 256;
                 for (int k = 0; k < ksteps; ++k) umma_f16_ts(d, a + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
                 umma_commit(&o_full[buf]);
+                ATC_TRACE(0, u, 2);                       // P.V of unit u issued
                 if ((u + 1) % upi == 0) umma_commit(&kv_empty[kvs]);   // last unit of the item: K / V stage reusable
                 if (u + 2 < n_units) {
                     mbar_wait(&s_free[buf], (u >> 1) & 1);
+                    ATC_TRACE(0, u, 3);                   // buffer of unit u drained
                     tcgen05_fence_after();
                     issue_qk(u + 2);
                 }
@@ -256,6 +271,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const int wrow0 = mt * 128 + quad * 32;       // first query row (within the image) of this warp
             const bool warp_valid = wrow0 < p.S;
             mbar_wait(&s_full[g], j & 1);
+            if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 0);       // S ready
             tcgen05_fence_after();
             float row_sum = 1.f;
             if (warp_valid) {
@@ -280,6 +296,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         if (nfull * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
                 }
                 const float mc = mx * c;
+                if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 1);   // pass 1 done
                 // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns.
                 //      Software-pipelined: the TMEM load of chunk i + 1 is in flight while chunk i is in the MUFU ----
                 float sum0 = 0.f, sum1 = 0.f;
@@ -328,10 +345,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
             tcgen05_fence_before();
             __syncwarp();
+            if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 2);       // pass 2 done
             if (lane == 0) mbar_arrive(&p_full[g]);
 
             // ---- O = P V is computed by the tensor core; scale by 1 / rowsum and store ----
             mbar_wait(&o_full[g], j & 1);
+            if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 3);       // O ready
             tcgen05_fence_after();
             if (warp_valid) {
                 const float inv = 1.0f / row_sum;
@@ -354,6 +373,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
             tcgen05_fence_before();
             __syncwarp();
+            if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 4);       // O drained
             if (lane == 0) mbar_arrive(&s_free[g]);     // TMEM buffer may be overwritten by the next QK^T
             if (warp_valid) {
                 const int cq = lane & 7;

@@ -377,6 +377,13 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     p.units_per_item = (S + 127) / 128;
     p.scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
     p.out = out;
+    p.trace = nullptr;
+#ifdef MCM_ATC_TRACE
+    static long long* trace_dev = nullptr;
+    if (!trace_dev) { cudaMalloc(&trace_dev, 3 * 16 * 8 * sizeof(long long)); }
+    cudaMemsetAsync(trace_dev, 0, 3 * 16 * 8 * sizeof(long long), st);
+    p.trace = trace_dev;
+#endif
     const int smem = atc_smem_bytes(p.keys_pad);
     static int attr_smem = 0;
     if (smem > attr_smem) {
@@ -398,6 +405,25 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
         return MCM_OK;
     }
     MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, p));
+#ifdef MCM_ATC_TRACE
+    {
+        static int dumped = 0;
+        if (dumped++ == 5) {   // a warm launch
+            long long t[3 * 16 * 8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(t, trace_dev, sizeof t, cudaMemcpyDeviceToHost);
+            long long t0 = t[0];
+            const char* names[3] = {"mma", "softmax_g0", "softmax_g1"};
+            for (int r = 0; r < 3; ++r)
+                for (int u = 0; u < 16; ++u) {
+                    printf("ATC_TRACE %s unit %2d:", names[r], u);
+                    for (int e = 0; e < 5; ++e) printf(" %8lld", t[(r * 16 + u) * 8 + e] ? t[(r * 16 + u) * 8 + e] - t0 : -1);
+                    printf("\n");
+                }
+            fflush(stdout);
+        }
+    }
+#endif
     h->launches++;
     return MCM_OK;
 }
