@@ -58,27 +58,34 @@ def main():
     eng.set_text_bank(synth.centred_prototype_bank(feats))
 
     def score_stream(n, seed, is_id):
+        """Images are defined per GLOBAL slab of `batch` images (seeded by the slab index), so the stream --
+        and therefore every score and metric -- is identical for any number of ranks."""
         lo, hi = parallel.shard_bounds(n, rank, world)
         out = torch.empty((hi - lo,), dtype=torch.float32, device=dev)
         gen = torch.Generator(device=dev)
-        for s in range(lo, hi, a.batch):
-            b = min(a.batch, hi - s)
-            gen.manual_seed(seed * 1_000_003 + s)            # slab seed depends on the GLOBAL index: sharding-invariant
-            x = torch.randn((b, 3, cfg.image_size, cfg.image_size), device=dev, generator=gen)
+        for k in range(lo // a.batch, -(-hi // a.batch) if hi > lo else 0):
+            s0 = k * a.batch
+            gen.manual_seed(seed * 1_000_003 + k)
+            x = torch.randn((a.batch, 3, cfg.image_size, cfg.image_size), device=dev, generator=gen)
             if is_id:
-                idx = (torch.arange(s, s + b, device=dev) % a.K)
+                idx = (torch.arange(s0, s0 + a.batch, device=dev) % a.K)
                 x = x * a.noise + protos[idx]
             else:
                 x = x * float(np.sqrt(1.0 + a.noise ** 2))
-            eng.score(x, T=a.T, score=a.score, out=out[s - lo:s - lo + b])
+            u, v = max(lo, s0), min(hi, s0 + a.batch)          # part of the slab owned by this rank
+            eng.score(x[u - s0:v - s0].contiguous(), T=a.T, score=a.score, out=out[u - lo:v - lo])
         return parallel.gather_scores(out, n)
 
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    import hashlib
+    digest = hashlib.sha1()
     in_score = score_stream(a.n_id, 1, True)
+    digest.update(in_score.tobytes())
     rows = []
     for j, n in enumerate(int(v) for v in a.ood.split(",")):
         out_score = score_stream(n, 10 + j, False)
+        digest.update(out_score.tobytes())
         auroc, aupr, fpr = metrics.get_measures(-in_score, -out_score)      # utils/detection_util.py:259
         rows.append(dict(n_ood=n, auroc=auroc, aupr=aupr, fpr95=float(fpr)))
     torch.cuda.synchronize()
@@ -88,6 +95,7 @@ def main():
         print(json.dumps(dict(model=a.model, K=a.K, n_gpus=world, n_id=a.n_id, sets=rows,
                               mean_auroc=float(np.mean([r["auroc"] for r in rows])),
                               mean_fpr95=float(np.mean([r["fpr95"] for r in rows])),
+                              score_sha1=digest.hexdigest(),   # identical for any number of ranks
                               images=n_total, seconds=dt, images_per_s=n_total / dt,
                               note="wall clock incl. on-device stream generation; bench.py is the timing instrument")))
     if world > 1:
