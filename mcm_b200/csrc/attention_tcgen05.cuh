@@ -19,6 +19,14 @@
 //                                                 O fp32 [128, 192)  (dead S columns by the time PV runs)
 // Padded keys (>= S) are masked to probability 0; padded query rows are computed and never stored.
 //
+// Measured (clock64 phase trace of one CTA, ViT-B/16 shape, tools/attn_sweep.py with the -DMCM_ATC_TRACE
+// build): one unit takes ~7.7 k cycles end to end -- row max 1.4 k, exp2 pass 3.1 k (the warp's own
+// instruction stream, MUFU 53 % busy), and ~3.2 k of hand-offs (barrier hops, issuing 13 P.V UMMAs,
+// draining O) -- with two units in flight per SM (TMEM holds two S buffers).  Tried and rejected, all
+// within +-5 %: software-pipelined TMEM loads, two threads per row (attention_tcgen05_split.cuh), one MMA
+// issuer warp per buffer, forcing the two groups out of phase.  96 us per layer call vs 293 us for the
+// mma.sync kernel; the next step is a third unit in flight (split the keys, rescale O in TMEM).
+//
 // qkv: fp16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)
 // out: fp16 [b * S, H * 64]      (== attn_output.transpose(1,2).reshape(B,S,D), HF:333)
 #pragma once
@@ -31,7 +39,7 @@
 
 namespace mcm {
 
-constexpr int kAtcThreads = 352;   // producer, MMA issuer 0, 8 softmax warps, MMA issuer 1
+constexpr int kAtcThreads = 320;
 constexpr int kAtcQStages = 3;
 constexpr int kAtcQBytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kAtcStagingBytes = 8 * 32 * 128; // 8 softmax warps x 32 rows x 64 fp16
@@ -93,13 +101,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // running max over one 32-key chunk of a score row (keys k0 .. k0 + 31; keys >= S are padding)
 __device__ __forceinline__ float atc_chunk_max(const uint32_t (&v)[32], int k0, int S, float mx) {
     if (k0 + 32 <= S) {
-        float m[4] = {mx, -INFINITY, -INFINITY, -INFINITY};   // four independent chains instead of one serial one
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) m[q] = fmaxf(m[q], fmaxf(__uint_as_float(v[e + 2 * q]), __uint_as_float(v[e + 2 * q + 1])));
-        }
-        mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+        for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
     } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e)
@@ -166,7 +169,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tma_prefetch_desc(&tmap_kv);
         for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], upi);   // one release per unit of the item (one per MMA issuer)
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
         }
@@ -201,50 +204,56 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 }
             }
         }
-    } else if (warp == 1 || warp == 10) {
+    } else if (warp == 1) {
         if (elect_one()) {
-            // ===== MMA issuers: warp 1 serves TMEM buffer 0 (even units), warp 10 buffer 1 (odd units), so a
-            //       wait on one buffer's softmax never delays the other buffer's P.V / QK^T =====
-            const int buf = (warp == 1) ? 0 : 1;
+            // ===== MMA issuer =====
             const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
             const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
             const uint32_t idesc_qk = make_idesc_f16(128, static_cast<uint32_t>(p.keys_pad));
             const uint32_t idesc_pv = make_idesc_f16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
             const int ksteps = p.keys_pad >> 4;
-            const uint32_t t_buf = tmem_base + buf * 256;
-            for (uint32_t u = buf; u < n_units; u += 2) {
-                const uint32_t iu = u / upi;                      // CTA-local item index of unit u
-                const int kvs = iu & 1, qs = u % kAtcQStages;
-                const uint32_t jb = u >> 1;                       // use count of this buffer
-                if (jb > 0) {                                     // previous unit's O must have been drained
-                    mbar_wait(&s_free[buf], (jb - 1) & 1);
-                    ATC_TRACE(0, u - 2, 3);
-                }
-                mbar_wait(&kv_full[kvs], (iu >> 1) & 1);
-                mbar_wait(&q_full[qs], (u / kAtcQStages) & 1);
+            auto issue_qk = [&](uint32_t v) {
+                const uint32_t iv = v / upi;                      // CTA-local item index of unit v
+                const int kvs = iv & 1, qs = v % kAtcQStages, buf = v & 1;
+                mbar_wait(&kv_full[kvs], (iv >> 1) & 1);
+                mbar_wait(&q_full[qs], (v / kAtcQStages) & 1);
                 tcgen05_fence_after();
-                {   // S = Q K^T
-                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(s_q + qs * kAtcQBytes), 16, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes), 16, 1024);
+                const uint64_t adesc = make_smem_desc_sw128(smem_u32(s_q + qs * kAtcQBytes), 16, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes), 16, 1024);
+                const uint32_t d = tmem_base + buf * 256;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(t_buf, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
-                    umma_commit(&q_empty[qs]);
-                    umma_commit(&s_full[buf]);
-                    ATC_TRACE(0, u, 0);
-                }
-                mbar_wait(&p_full[buf], jb & 1);
-                ATC_TRACE(0, u, 1);
+                for (int k = 0; k < 4; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+                umma_commit(&q_empty[qs]);
+                umma_commit(&s_full[buf]);
+                ATC_TRACE(0, v, 0);                       // QK^T of unit v issued
+            };
+            if (n_units > 0) issue_qk(0);
+            if (n_units > 1) issue_qk(1);
+            for (uint32_t u = 0; u < n_units; ++u) {
+                const int buf = u & 1;
+                const uint32_t iu = u / upi;
+                const int kvs = iu & 1;
+                mbar_wait(&p_full[buf], (u >> 1) & 1);
+                ATC_TRACE(0, u, 1);                       // P of unit u ready
                 tcgen05_fence_after();
-                // O = P V.  V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
+                // V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
                 const uint64_t vdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes + kv_bytes), 1024, 1024);
-                for (int k = 0; k < ksteps; ++k) umma_f16_ts(t_buf + 128, t_buf + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
+                const uint32_t d = tmem_base + buf * 256 + 128;
+                const uint32_t a = tmem_base + buf * 256;
+                for (int k = 0; k < ksteps; ++k) umma_f16_ts(d, a + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
                 umma_commit(&o_full[buf]);
-                umma_commit(&kv_empty[kvs]);                      // this unit no longer needs the item's K / V stage
-                ATC_TRACE(0, u, 2);
+                ATC_TRACE(0, u, 2);                       // P.V of unit u issued
+                if ((u + 1) % upi == 0) umma_commit(&kv_empty[kvs]);   // last unit of the item: K / V stage reusable
+                if (u + 2 < n_units) {
+                    mbar_wait(&s_free[buf], (u >> 1) & 1);
+                    ATC_TRACE(0, u, 3);                   // buffer of unit u drained
+                    tcgen05_fence_after();
+                    issue_qk(u + 2);
+                }
             }
         }
-    } else if (warp >= 2) {
-        // ===== softmax / epilogue groups (warps 2-9) =====
+    } else {
+        // ===== softmax / epilogue groups =====
         const int g = (warp - 2) >> 2;       // group = TMEM buffer
         const int quad = warp & 3;           // TMEM lane quadrant
         const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
@@ -255,6 +264,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const int nfull = p.keys_pad >> 5;
         const bool rem16 = (p.keys_pad & 16) != 0;
         const float c = p.scale_log2e;
+        // Stagger the two groups by half a period: group 1 starts its first softmax only when group 0 has
+        // finished its first one, so from then on one group is in the MUFU-bound softmax while the tensor
+        // core serves the other group's P.V / next QK^T (the MMA warp issues in exactly that order).
+#ifndef MCM_ATC_NO_STAGGER
+        if (g == 1 && n_units > 1) mbar_wait(&p_full[0], 0);
+#endif
         for (uint32_t u = g; u < n_units; u += 2) {
             const uint32_t j = u >> 1;
             const uint32_t iu = u / upi;
