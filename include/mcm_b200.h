@@ -86,7 +86,8 @@ const char* mcm_last_error(const McmHandle* h);
 int mcm_load_weight(McmHandle* h, const char* hf_key, const float* data, int64_t numel, int32_t* used);
 
 /* Verify that every tensor of the vision path arrived and convert/pack them for the kernels
- * (fp16 GEMM operands, fused QKV weight, padded patch filter).  Must precede any compute call. */
+ * (fp16 GEMM operands, fused QKV weight, padded patch filter, layer_norm1 / layer_norm2 folded into
+ * the q/k/v and fc1 weights).  Must precede any compute call; call it again after re-loading tensors. */
 int mcm_finalize_weights(McmHandle* h);
 
 /* Install the pre-encoded prompt bank: `bank` is [K,P] fp32 (host or device), one row per entry
@@ -150,6 +151,24 @@ int32_t mcm_abi_version(void);
  * epi 2: out f32  = resid + acc + bias    (resid may alias out) */
 int mcm_dbg_gemm(McmHandle* h, const void* a_f16, const void* w_f16, const float* bias, const float* resid,
                  void* out, int32_t M, int32_t N, int32_t K, int32_t epi, void* stream);
+/* The LayerNorm-folded projections the forward actually runs (csrc/gemm_tcgen05.cuh): layer_norm1 / layer_norm2
+ * (HF:371,380) never materialise; the projection reads the RAW fp16 residual rows and its epilogue applies the row
+ * statistics.
+ *   mcm_dbg_fold_ln      : W f32 [N,K], gamma/beta [K], bias [N] -> w16 = fp16(gamma o W), c[N] = row sums of w16,
+ *                          d[N] = bias + beta @ W^T
+ *   mcm_dbg_gemm_resid_ln: out f32 = resid + A W^T + bias (resid may alias out), out16 = fp16(out), and
+ *                          stats = float2 [*parts][M] partial (sum, sum of squares) over column slices of out
+ *                          (allocate N / 64 parts; *parts returns how many were written)
+ *   mcm_dbg_gemm_ln      : out fp16 = [quick_gelu](rstd * (A w16^T) - rstd * mu * c + d) with mu / rstd of every
+ *                          row taken from `stats` (float2 [parts][M]) over `row_len` elements, eps from the config */
+int mcm_dbg_fold_ln(McmHandle* h, const float* w, const float* gamma, const float* beta, const float* bias, void* w16,
+                    float* c, float* d, int32_t N, int32_t K, void* stream);
+int mcm_dbg_gemm_ln(McmHandle* h, const void* a_f16, const void* w16, const float* d, const float* c, const float* stats,
+                    int32_t parts, int32_t row_len, void* out_f16, int32_t M, int32_t N, int32_t K, int32_t gelu,
+                    void* stream);
+int mcm_dbg_gemm_resid_ln(McmHandle* h, const void* a_f16, const void* w_f16, const float* bias, const float* resid,
+                          float* out, void* out16, float* stats, int32_t M, int32_t N, int32_t K, int32_t* parts,
+                          void* stream);
 /* nn.LayerNorm over the last dim (HF:359-361): x f32 [M,D] -> out fp16 (out_f16 != 0) or f32. */
 int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* gamma, const float* beta, void* out, int32_t M,
                       int32_t D, float eps, int32_t out_f16, void* stream);

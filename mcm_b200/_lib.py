@@ -51,6 +51,11 @@ SIGNATURES = {
     "mcm_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "mcm_flops_per_image": (C.c_double, [C.POINTER(McmConfig), C.c_int32]),
     "mcm_dbg_gemm": (C.c_int, [_H, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "mcm_dbg_fold_ln": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "mcm_dbg_gemm_ln": (C.c_int, [_H, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, _P]),
+    "mcm_dbg_gemm_resid_ln": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_int32), _P]),
     "mcm_dbg_layernorm": (C.c_int, [_H, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
     "mcm_dbg_attention": (C.c_int, [_H, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mcm_dbg_tail": (C.c_int, [_H, _P, C.c_int32, C.c_float, C.c_int32, _P, _P, _P]),

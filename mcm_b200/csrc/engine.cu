@@ -6,9 +6,11 @@
 // of launches on the caller's stream; nothing is allocated after mcm_create.
 //
 // Path per batch (reference: utils/detection_util.py:225-248 -> HF modeling_clip.py:829-863):
-//   patchify -> patch GEMM(+pos) -> embed_finish(CLS, pre-LN, LN1) ->
-//   L x [ QKV GEMM -> attention -> out-proj GEMM(+residual) -> LN2 -> fc1 GEMM(+quick_gelu)
-//         -> fc2 GEMM(+residual) -> LN1 of the next layer ] -> tail (post-LN, projection, MCM score)
+//   patchify -> patch GEMM(+pos) -> embed_finish(CLS, pre-LN; fp16 copy + row statistics) ->
+//   L x [ QKV GEMM (LN1 folded) -> attention -> out-proj GEMM(+residual, fp16 copy, row statistics)
+//         -> fc1 GEMM (LN2 folded, +quick_gelu) -> fc2 GEMM(+residual, fp16 copy, row statistics) ]
+//   -> tail (post-LN, projection, MCM score)
+// layer_norm1 / layer_norm2 never run as kernels: see the LayerNorm-folding note in gemm_tcgen05.cuh.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -54,7 +56,9 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct LayerWeights {
-    op16_t *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    op16_t *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;   // wqkv / w1 hold gamma o W (LayerNorm fold)
+    float *wqkv32 = nullptr, *w132 = nullptr;   // fp32 masters of the two folded weights (refolded by every finalize)
+    float *cqkv = nullptr, *dqkv = nullptr, *c1 = nullptr, *d1 = nullptr;   // fold vectors c, d (gemm_tcgen05.cuh)
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
     CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
@@ -66,8 +70,6 @@ struct McmHandle {
     McmConfig cfg{};
     int G = 0, Np = 0, S = 0, D = 0, H = 0, F = 0, P = 0, L = 0, Kp = 0, Kpatch = 0;
     int num_sms = 0;
-    bool gemm_1cta = false;  // debug A/B switch (env MCM_GEMM_1CTA=1): single-CTA 128 x BLOCK_N tiles instead of CTA pairs
-    int gemm_pairs = 1;      // CTA pairs per cluster (env MCM_GEMM_PAIRS=2: 4-CTA clusters with W-tile multicast)
     int64_t m_pad = 0, mp_pad = 0;  // padded token rows / patch rows for max_batch
     std::string err;
 
@@ -88,11 +90,13 @@ struct McmHandle {
     int K = 0;
 
     // workspace
-    op16_t *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
-    float* x = nullptr;
+    op16_t *patches = nullptr, *xh = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
+    float* x = nullptr;                                       // fp32 residual stream; xh = its fp16 copy (GEMM A operand)
+    float2* stats = nullptr;                                  // [stats_parts][m_pad] partial (sum, sum of squares) of the rows of x
+    int stats_parts = 0;
     float* x_cls = nullptr;                                   // [pad128(max_batch), D] CLS rows of the last layer
     float *t_ln = nullptr, *t_feat = nullptr, *t_logit = nullptr;   // tail scratch: [max_batch, D | P | K]
-    CUtensorMap tm_patches, tm_xn, tm_attn, tm_hid;
+    CUtensorMap tm_patches, tm_xh, tm_attn, tm_hid;
     CUtensorMap tm_qkv_q, tm_qkv_kv;   // attention: 128-row Q boxes / keys_pad-row K,V boxes over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
     bool attn_split = false;           // env MCM_ATTN_SPLIT=1: two threads per query row (16 softmax warps), keys_pad <= 208
@@ -167,6 +171,28 @@ struct ProfScope {
             return fail(h, MCM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// fp16 [rows, cols] output of a GEMM epilogue: 32-row x 32-column boxes (64 B inner dimension, 64-byte swizzle =
+// the layout of the epilogue's staging tile)
+int make_tmap_out16(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * sizeof(op16_t)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+#ifdef MCM_OP_BF16
+    constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+    constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
+    CUresult r = enc(m, kOpType, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled (output) failed (%d) rows=%llu cols=%llu", (int)r,
+                    (unsigned long long)rows, (unsigned long long)cols);
+    return MCM_OK;
+}
+
 int make_tmap(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -224,61 +250,42 @@ inline int cuda_rc(McmHandle* h, cudaError_t e) {
 inline int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
 template <int BN, int EPI>
-int launch_gemm_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    static bool attr_done = false;  // per instantiation; one device per process in practice
-    auto kern = gemm_f16_tn_kernel<BN, EPI>;
+int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
+                   cudaStream_t st) {
+    static bool attr_done = false;   // per instantiation; one device per process in practice
+    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI>;
     if (!attr_done) {
-        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
         attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    MCM_CUDA(h, launch_k(kern, dim3(grid), dim3(kGemmThreads), GemmSmem<BN>::kTotal, st, 1, ta, tb, p));
+    const int clusters = std::min(tiles, h->num_sms / 2);   // persistent: one CTA pair per TPC
+    MCM_CUDA(h, launch_k(kern, dim3(2 * clusters), dim3(EpiTraits<EPI>::kThreads), Gemm2Smem<BN>::kTotal, st, 2, ta, tb, tout, p));
     h->launches++;
     return MCM_OK;
 }
 
-template <int BN, int EPI, int PAIRS>
-int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    static int max_clusters = 0;   // co-resident clusters of this instantiation (persistent grid size)
-    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI, PAIRS>;
-    constexpr int kCluster = 2 * PAIRS;
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(kGemm2Threads);
-    cfg.dynamicSmemBytes = Gemm2Smem<BN>::kTotal;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (max_clusters == 0) {
-        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
-        // clusters of 4 do not tile every GPC: ask the driver how many can be resident at once
-        cfg.gridDim = dim3(kCluster * (h->num_sms / kCluster));
-        int n = 0;
-        MCM_CUDA(h, cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-        if (n <= 0) return fail(h, MCM_ECUDA, "no %d-CTA cluster of the GEMM kernel fits on this device", kCluster);
-        max_clusters = std::min(n, h->num_sms / kCluster);
-    }
-    const int tiles = ((p.m_tiles + PAIRS - 1) / PAIRS) * p.n_tiles;
-    const int clusters = std::min(tiles, max_clusters);
-    MCM_CUDA(h, launch_k(kern, dim3(kCluster * clusters), dim3(kGemm2Threads), Gemm2Smem<BN>::kTotal, st, kCluster, ta, tb, p));
-    h->launches++;
-    return MCM_OK;
-}
+// LayerNorm-fold side of a GEMM launch (gemm_tcgen05.cuh): consumer (EPI_LN_*) or producer (EPI_BIAS_RESID_F32_LN) fields
+struct GemmLnArgs {
+    const float* colsum = nullptr;
+    const float2* stats_in = nullptr;
+    int stats_parts = 0;
+    op16_t* out16 = nullptr;
+    float2* stats_out = nullptr;
+    int stats_ld = 0;
+    int row_len = 1;
+};
 
 // C[M, N] = A[M, K] W[N, K]^T with fused epilogue.  M rows valid; A's tensor map covers >= ceil(M/128)*128 rows.
 int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi,
-                const float* bias, void* out, const float* resid, const float* pos, int np, int seq, cudaStream_t st) {
+                const float* bias, void* out, const float* resid, const float* pos, int np, int seq, cudaStream_t st,
+                const GemmLnArgs& ln = GemmLnArgs()) {
     if (M <= 0) return MCM_OK;
     if (N % 128 != 0 || K % kGemmBlockK != 0)
         return fail(h, MCM_EUNSUPPORTED, "GEMM shape N=%d (multiple of 128) K=%d (multiple of 64) unsupported", N, K);
     const int bn = gemm_block_n(N);
     GemmParams p{};
-    p.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    p.m_tiles = (M + kGemm2TileM - 1) / kGemm2TileM;
     p.n_tiles = N / bn;
     p.k_blocks = K / kGemmBlockK;
     p.m_valid = M;
@@ -289,21 +296,36 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     p.pos = pos;
     p.np = np;
     p.seq = seq;
+    p.colsum = ln.colsum;
+    p.stats_in = ln.stats_in;
+    p.stats_parts = ln.stats_parts;
+    p.stats_ld = ln.stats_ld;
+    p.inv_k = 1.0f / static_cast<float>(ln.row_len);
+    p.eps = h->cfg.eps;
+    p.out16 = ln.out16;
+    p.stats_out = ln.stats_out;
+    // fp16 outputs leave through TMA bulk stores (measured 6-9 % faster on the K = 768 projections than LSU stores of the
+    // same staging tile: the stores share the SM <-> L2 path with the operand loads); MCM_GEMM_TMA_STORE=0 is the A/B switch
+    static const bool tma_store = [] { const char* e = getenv("MCM_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+    CUtensorMap tout = ta;   // placeholder for the kinds that do not store through TMA
+    const bool f16_out = epi == EPI_BIAS_F16 || epi == EPI_BIAS_QGELU_F16 || epi == EPI_LN_F16 || epi == EPI_LN_QGELU_F16;
+    p.tma_store = (tma_store && f16_out) ? 1 : 0;
+    if (p.tma_store) {
+        int rc = make_tmap_out16(h, &tout, out, M, N);   // exactly M rows: the TMA unit clips the last tile
+        if (rc) return rc;
+    }
+    static const int dbg_skip = [] { const char* e = getenv("MCM_GEMM_DBG_SKIP"); return e ? atoi(e) : 0; }();
+    p.dbg_skip = dbg_skip;
     ProfScope prof(h, prof_kind, st);
-    if (!h->gemm_1cta) p.m_tiles = (M + kGemm2TileM - 1) / kGemm2TileM;
-#define MCM_GEMM_CASE(BN, E)                                                     \
-    if (bn == BN && epi == E)                                                    \
-        return h->gemm_1cta ? launch_gemm_t<BN, E>(h, ta, tb, p, st)                                         \
-               : h->gemm_pairs == 2 ? launch_gemm2_t<BN, E, 2>(h, ta, tb, p, st)                             \
-                                    : launch_gemm2_t<BN, E, 1>(h, ta, tb, p, st);
-    MCM_GEMM_CASE(256, EPI_BIAS_F16)
-    MCM_GEMM_CASE(256, EPI_BIAS_QGELU_F16)
-    MCM_GEMM_CASE(256, EPI_BIAS_RESID_F32)
-    MCM_GEMM_CASE(256, EPI_POS_F32)
-    MCM_GEMM_CASE(128, EPI_BIAS_F16)
-    MCM_GEMM_CASE(128, EPI_BIAS_QGELU_F16)
-    MCM_GEMM_CASE(128, EPI_BIAS_RESID_F32)
-    MCM_GEMM_CASE(128, EPI_POS_F32)
+#define MCM_GEMM_CASE(E)                                                     \
+    if (epi == E) return bn == 256 ? launch_gemm2_t<256, E>(h, ta, tb, tout, p, st) : launch_gemm2_t<128, E>(h, ta, tb, tout, p, st);
+    MCM_GEMM_CASE(EPI_BIAS_F16)
+    MCM_GEMM_CASE(EPI_BIAS_QGELU_F16)
+    MCM_GEMM_CASE(EPI_BIAS_RESID_F32)
+    MCM_GEMM_CASE(EPI_POS_F32)
+    MCM_GEMM_CASE(EPI_LN_F16)
+    MCM_GEMM_CASE(EPI_LN_QGELU_F16)
+    MCM_GEMM_CASE(EPI_BIAS_RESID_F32_LN)
 #undef MCM_GEMM_CASE
     return fail(h, MCM_EINVAL, "unknown GEMM epilogue %d", epi);
 }
@@ -459,12 +481,11 @@ int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
     if (rc) return rc;
     const int M = b * h->S;
     const int grid = (M + (kRowThreads / 32) - 1) / (kRowThreads / 32);
-    const LayerWeights& l0 = h->layers[0];
     ProfScope prof(h, MCM_PROF_EMBED_FINISH, st);
     rc = dispatch_vec(h, h->D, [&](auto vec) {
         constexpr int V = decltype(vec)::value;
-        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xn, h->cls, h->pos,
-                                   h->pre_g, h->pre_b, l0.ln1g, l0.ln1b, M, h->S, h->cfg.eps));
+        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xh, h->stats, h->cls,
+                                   h->pos, h->pre_g, h->pre_b, M, h->S, h->cfg.eps));
     });
     if (rc) return rc;
     MCM_CUDA(h, cudaGetLastError());
@@ -480,35 +501,47 @@ int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st, con
     const int M = b * h->S, D = h->D, F = h->F;
     *pooled = h->x;
     *pooled_stride = static_cast<size_t>(h->S) * D;
+    const int ld = static_cast<int>(h->m_pad);
     for (int i = 0; i < h->L; ++i) {
         const LayerWeights& w = h->layers[i];
-        // xn = LN1(x) is already in place (embed_finish for layer 0, end of the previous layer otherwise)
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xn, w.tm_wqkv, M, 3 * D, D, EPI_BIAS_F16, w.bqkv, h->qkv, nullptr, nullptr, 0, 0, st))) return rc;
-        if (i + 1 == h->L && h->cls_shortcut) {
-            // only query row 0 of every image is consumed after this point (HF:685)
+        const bool last = i + 1 == h->L;
+        // consumer side of the LayerNorm fold: xh holds the raw fp16 rows of x, stats their partial sums
+        // (one part after embed_finish, one per 128-column half tile after an out_proj / fc2 epilogue)
+        GemmLnArgs ln1, ln2, prod;
+        ln1.colsum = w.cqkv;
+        ln1.stats_in = h->stats;
+        ln1.stats_parts = i == 0 ? 1 : h->stats_parts;
+        ln1.stats_ld = ld;
+        ln1.row_len = D;
+        ln2 = ln1;
+        ln2.colsum = w.c1;
+        ln2.stats_parts = h->stats_parts;
+        prod.out16 = h->xh;
+        prod.stats_out = h->stats;
+        prod.stats_ld = ld;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xh, w.tm_wqkv, M, 3 * D, D, EPI_LN_F16, w.dqkv, h->qkv, nullptr, nullptr, 0, 0, st, ln1))) return rc;
+        if (last && h->cls_shortcut) {
+            // only query row 0 of every image is consumed after this point (HF:685); the b CLS rows move to
+            // x_cls, and xh / stats (free once the QKV projection has run) carry their fp16 copy and statistics
             {
                 ProfScope prof(h, MCM_PROF_ATTENTION, st);
                 MCM_CUDA(h, launch_k(attention_cls_kernel, dim3((b * h->H + kClsWarps - 1) / kClsWarps), dim3(kClsWarps * 32), 0,
                                      st, 1, h->qkv, h->x, h->attn, h->x_cls, b, h->S, h->H, 0.125f));
             }
             h->launches++;
-            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st))) return rc;
-            if ((rc = launch_layernorm(h, h->x_cls, w.ln2g, w.ln2b, h->xn, b, D, h->cfg.eps, true, st))) return rc;
-            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, b, F, D, EPI_BIAS_QGELU_F16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st, prod))) return rc;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, b, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
             if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, b, D, F, EPI_BIAS_RESID_F32, w.b2, h->x_cls, h->x_cls, nullptr, 0, 0, st))) return rc;
             *pooled = h->x_cls;
             *pooled_stride = D;
             break;
         }
         if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32, w.bo, h->x, h->x, nullptr, 0, 0, st))) return rc;
-        if ((rc = launch_layernorm(h, h->x, w.ln2g, w.ln2b, h->xn, M, D, h->cfg.eps, true, st))) return rc;
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xn, w.tm_w1, M, F, D, EPI_BIAS_QGELU_F16, w.b1, h->hid, nullptr, nullptr, 0, 0, st))) return rc;
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, EPI_BIAS_RESID_F32, w.b2, h->x, h->x, nullptr, 0, 0, st))) return rc;
-        if (i + 1 < h->L) {
-            const LayerWeights& n = h->layers[i + 1];
-            if ((rc = launch_layernorm(h, h->x, n.ln1g, n.ln1b, h->xn, M, D, h->cfg.eps, true, st))) return rc;
-        }
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x, h->x, nullptr, 0, 0, st, prod))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, M, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
+        // the last layer's output only feeds the pooled post-LN of the tail: no fp16 copy, no statistics
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, last ? EPI_BIAS_RESID_F32 : EPI_BIAS_RESID_F32_LN, w.b2,
+                              h->x, h->x, nullptr, 0, 0, st, last ? GemmLnArgs() : prod))) return rc;
     }
     return MCM_OK;
 }
@@ -536,7 +569,7 @@ int dev_alloc(McmHandle* h, T** p, size_t n, bool zero) {
 
 // where one HF tensor goes
 struct Dest {
-    float* f32 = nullptr;            // fp32 destination, or
+    float* f32 = nullptr;            // fp32 destination (also the fp32 master of a LayerNorm-folded weight), or
     op16_t* fp16 = nullptr;   // fp16 destination (converted)
     int64_t rows = 0;
     int cols = 0, dst_ld = 0;
@@ -591,15 +624,15 @@ bool resolve_key(McmHandle* h, const char* key, Dest* d) {
         case 1: return f32(w.ln1b, D, slot);
         case 2: return f32(w.ln2g, D, slot);
         case 3: return f32(w.ln2b, D, slot);
-        case 4: return b16(w.wqkv, D, D, D, slot);
+        case 4: return f32(w.wqkv32, (int64_t)D * D, slot);   // q/k/v and fc1 weights are folded with their LayerNorm at finalize
         case 5: return f32(w.bqkv, D, slot);
-        case 6: return b16(w.wqkv + (size_t)D * D, D, D, D, slot);
+        case 6: return f32(w.wqkv32 + (size_t)D * D, (int64_t)D * D, slot);
         case 7: return f32(w.bqkv + D, D, slot);
-        case 8: return b16(w.wqkv + (size_t)2 * D * D, D, D, D, slot);
+        case 8: return f32(w.wqkv32 + (size_t)2 * D * D, (int64_t)D * D, slot);
         case 9: return f32(w.bqkv + 2 * D, D, slot);
         case 10: return b16(w.wo, D, D, D, slot);
         case 11: return f32(w.bo, D, slot);
-        case 12: return b16(w.w1, F, D, D, slot);
+        case 12: return f32(w.w132, (int64_t)F * D, slot);
         case 13: return f32(w.b1, F, slot);
         case 14: return b16(w.w2, D, F, F, slot);
         case 15: return f32(w.b2, D, slot);
@@ -665,12 +698,6 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     h->Kp = (h->Kpatch + kGemmBlockK - 1) / kGemmBlockK * kGemmBlockK;
     h->m_pad = (static_cast<int64_t>(cfg->max_batch) * h->S + 255) / 256 * 256;
     h->mp_pad = (static_cast<int64_t>(cfg->max_batch) * h->Np + 255) / 256 * 256;
-    {
-        const char* e = getenv("MCM_GEMM_1CTA");
-        h->gemm_1cta = e && e[0] == '1';
-        const char* e2 = getenv("MCM_GEMM_PAIRS");
-        h->gemm_pairs = (e2 && e2[0] == '2') ? 2 : 1;
-    }
     const int D = h->D, F = h->F;
 
 #define MCM_TRY(expr)               \
@@ -697,6 +724,12 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         MCM_TRY(dev_alloc(h, &w.wo, (size_t)D * D, false));
         MCM_TRY(dev_alloc(h, &w.w1, (size_t)F * D, false));
         MCM_TRY(dev_alloc(h, &w.w2, (size_t)D * F, false));
+        MCM_TRY(dev_alloc(h, &w.wqkv32, (size_t)3 * D * D, false));
+        MCM_TRY(dev_alloc(h, &w.w132, (size_t)F * D, false));
+        MCM_TRY(dev_alloc(h, &w.cqkv, (size_t)3 * D, false));
+        MCM_TRY(dev_alloc(h, &w.dqkv, (size_t)3 * D, false));
+        MCM_TRY(dev_alloc(h, &w.c1, F, false));
+        MCM_TRY(dev_alloc(h, &w.d1, F, false));
         MCM_TRY(dev_alloc(h, &w.bqkv, (size_t)3 * D, false));
         MCM_TRY(dev_alloc(h, &w.bo, D, false));
         MCM_TRY(dev_alloc(h, &w.b1, F, false));
@@ -705,14 +738,14 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         MCM_TRY(dev_alloc(h, &w.ln1b, D, false));
         MCM_TRY(dev_alloc(h, &w.ln2g, D, false));
         MCM_TRY(dev_alloc(h, &w.ln2b, D, false));
-        const uint32_t wdiv = h->gemm_1cta ? 1 : 2 * h->gemm_pairs;   // each CTA of a cluster loads 1/2 or 1/4 of the W tile
+        const uint32_t wdiv = 2;   // each CTA of a pair loads half of the W tile
         const uint32_t bnD = gemm_block_n(D) / wdiv, bn3D = gemm_block_n(3 * D) / wdiv, bnF = gemm_block_n(F) / wdiv;
         MCM_TRY(make_tmap(h, &w.tm_wqkv, w.wqkv, 3 * D, D, bn3D));
         MCM_TRY(make_tmap(h, &w.tm_wo, w.wo, D, D, bnD));
         MCM_TRY(make_tmap(h, &w.tm_w1, w.w1, F, D, bnF));
         MCM_TRY(make_tmap(h, &w.tm_w2, w.w2, D, F, bnD));
     }
-    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D) / (h->gemm_1cta ? 1 : 2 * h->gemm_pairs)));
+    MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D) / 2));
     h->loaded.assign(SLOT_GLOBALS + 16 * h->L, 0);
     h->stage_elems = (size_t)std::max(std::max((size_t)F * D, (size_t)D * h->Kpatch), std::max((size_t)h->S * D, (size_t)h->P * D));
     MCM_TRY(dev_alloc(h, &h->stage, h->stage_elems, false));
@@ -721,7 +754,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     // outputs are masked by m_valid)
     MCM_TRY(dev_alloc(h, &h->patches, (size_t)h->mp_pad * h->Kp, true));
     MCM_TRY(dev_alloc(h, &h->x, (size_t)h->m_pad * D, true));
-    MCM_TRY(dev_alloc(h, &h->xn, (size_t)h->m_pad * D, true));
+    MCM_TRY(dev_alloc(h, &h->xh, (size_t)h->m_pad * D, true));
+    h->stats_parts = 2 * (D / gemm_block_n(D));   // one partial per half tile of a GEMM with N = D
+    MCM_TRY(dev_alloc(h, &h->stats, (size_t)h->stats_parts * h->m_pad, true));
     MCM_TRY(dev_alloc(h, &h->qkv, (size_t)h->m_pad * 3 * D, true));
     MCM_TRY(dev_alloc(h, &h->attn, (size_t)h->m_pad * D, true));
     MCM_TRY(dev_alloc(h, &h->hid, (size_t)h->m_pad * F, true));
@@ -729,7 +764,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(dev_alloc(h, &h->t_ln, (size_t)cfg->max_batch * D, false));
     MCM_TRY(dev_alloc(h, &h->t_feat, (size_t)cfg->max_batch * h->P, false));
     MCM_TRY(make_tmap(h, &h->tm_patches, h->patches, h->mp_pad, h->Kp, kGemmBlockM));
-    MCM_TRY(make_tmap(h, &h->tm_xn, h->xn, h->m_pad, D, kGemmBlockM));
+    MCM_TRY(make_tmap(h, &h->tm_xh, h->xh, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_attn, h->attn, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_hid, h->hid, h->m_pad, F, kGemmBlockM));
     {
@@ -756,8 +791,10 @@ void mcm_destroy(McmHandle* h) {
     for (auto& w : h->layers) {
         fr(w.wqkv); fr(w.wo); fr(w.w1); fr(w.w2); fr(w.bqkv); fr(w.bo); fr(w.b1); fr(w.b2);
         fr(w.ln1g); fr(w.ln1b); fr(w.ln2g); fr(w.ln2b);
+        fr(w.wqkv32); fr(w.w132); fr(w.cqkv); fr(w.dqkv); fr(w.c1); fr(w.d1);
     }
-    fr(h->stage); fr(h->bank); fr(h->patches); fr(h->x); fr(h->xn); fr(h->qkv); fr(h->attn); fr(h->hid);
+    fr(h->stats);
+    fr(h->stage); fr(h->bank); fr(h->patches); fr(h->x); fr(h->xh); fr(h->qkv); fr(h->attn); fr(h->hid);
     fr(h->img_buf[0]); fr(h->img_buf[1]); fr(h->scores_buf);
     fr(h->x_cls); fr(h->t_ln); fr(h->t_feat); fr(h->t_logit);
     for (int i = 0; i < 2; ++i) {
@@ -808,6 +845,12 @@ int mcm_finalize_weights(McmHandle* h) {
         return fail(h, MCM_ESTATE, "weight vision_model.encoder.layers.%d.%s was never loaded", li, kLayerNames[which]);
     }
     MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    // LayerNorm fold (gemm_tcgen05.cuh): W' = fp16(gamma o W), c = row sums of W', d = beta @ W^T + b
+    for (auto& w : h->layers) {
+        fold_ln_weight_kernel<<<(3 * h->D + 7) / 8, 256>>>(w.wqkv32, w.ln1g, w.ln1b, w.bqkv, w.wqkv, w.cqkv, w.dqkv, 3 * h->D, h->D);
+        fold_ln_weight_kernel<<<(h->F + 7) / 8, 256>>>(w.w132, w.ln2g, w.ln2b, w.b1, w.w1, w.c1, w.d1, h->F, h->D);
+    }
+    MCM_CUDA(h, cudaGetLastError());
     MCM_CUDA(h, cudaDeviceSynchronize());
     h->finalized = true;
     return MCM_OK;
@@ -954,8 +997,56 @@ int mcm_dbg_gemm(McmHandle* h, const void* a, const void* w, const float* bias, 
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
-    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / (h->gemm_1cta ? 1 : 2 * h->gemm_pairs)))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / 2))) return rc;
     return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, epi, bias, out, resid, nullptr, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int mcm_dbg_fold_ln(McmHandle* h, const float* w, const float* gamma, const float* beta, const float* bias, void* w16, float* c,
+                    float* d, int32_t N, int32_t K, void* stream) {
+    if (!h || !w || !gamma || !beta || !bias || !w16 || !c || !d) return fail(h, MCM_EINVAL, "mcm_dbg_fold_ln: NULL argument");
+    if (N <= 0 || K <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_fold_ln: N and K must be positive");
+    fold_ln_weight_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, gamma, beta, bias, static_cast<op16_t*>(w16), c,
+                                                                                     d, N, K);
+    MCM_CUDA(h, cudaGetLastError());
+    return MCM_OK;
+}
+
+int mcm_dbg_gemm_ln(McmHandle* h, const void* a, const void* w, const float* d, const float* c, const float* stats, int32_t parts,
+                    int32_t row_len, void* out, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream) {
+    if (!h || !a || !w || !d || !c || !stats || !out) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_ln: NULL argument");
+    if (M <= 0 || parts <= 0 || row_len <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_ln: M, parts and row_len must be positive");
+    if (N % 128 != 0 || K % 64 != 0) return fail(h, MCM_EUNSUPPORTED, "mcm_dbg_gemm_ln: N %% 128 and K %% 64 must be 0");
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / 2))) return rc;
+    GemmLnArgs ln;
+    ln.colsum = c;
+    ln.stats_in = reinterpret_cast<const float2*>(stats);
+    ln.stats_parts = parts;
+    ln.stats_ld = M;
+    ln.row_len = row_len;
+    return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, gelu ? EPI_LN_QGELU_F16 : EPI_LN_F16, d, out, nullptr, nullptr, 0, 0,
+                       static_cast<cudaStream_t>(stream), ln);
+}
+
+int mcm_dbg_gemm_resid_ln(McmHandle* h, const void* a, const void* w, const float* bias, const float* resid, float* out, void* out16,
+                          float* stats, int32_t M, int32_t N, int32_t K, int32_t* parts, void* stream) {
+    if (!h || !a || !w || !bias || !resid || !out || !out16 || !stats || !parts)
+        return fail(h, MCM_EINVAL, "mcm_dbg_gemm_resid_ln: NULL argument");
+    if (M <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_resid_ln: M must be positive");
+    if (N % 128 != 0 || K % 64 != 0) return fail(h, MCM_EUNSUPPORTED, "mcm_dbg_gemm_resid_ln: N %% 128 and K %% 64 must be 0");
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / 2))) return rc;
+    *parts = 2 * (N / gemm_block_n(N));
+    GemmLnArgs ln;
+    ln.out16 = static_cast<op16_t*>(out16);
+    ln.stats_out = reinterpret_cast<float2*>(stats);
+    ln.stats_ld = M;
+    return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, EPI_BIAS_RESID_F32_LN, bias, out, resid, nullptr, 0, 0,
+                       static_cast<cudaStream_t>(stream), ln);
 }
 
 int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float* b, void* out, int32_t M, int32_t D,

@@ -30,10 +30,25 @@
 
 namespace mcm {
 
-constexpr int kGemm2Threads = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
-constexpr int kGemm2EpiWarps = 8;    // two per TMEM lane quadrant (= per SM sub-partition): one column half each
 constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
-constexpr int kStgLd = 32;           // staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
+constexpr int kMaxStatsParts = 8;    // LayerNorm fold: partial row statistics per row (width <= 1024: 2 per 256-column tile)
+constexpr int kStgLd = 32;           // fp32 staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
+
+// What an epilogue kind implies.  fp16-output epilogues are instruction-latency bound (TMEM load ->
+// math -> staging transpose -> store is one dependent chain per 32-column chunk), so they run on 16
+// warps (four per SM sub-partition, one 64-column slice of the tile each); the fp32 residual epilogues
+// are bound by the HBM round trip of the residual rows and run on 8 warps with the NEXT chunk's
+// residual already in flight (the register budget of 8 warps allows the double buffer).
+template <int EPI>
+struct EpiTraits {
+    static constexpr bool kLn = (EPI == EPI_LN_F16 || EPI == EPI_LN_QGELU_F16);
+    static constexpr bool kGelu = (EPI == EPI_BIAS_QGELU_F16 || EPI == EPI_LN_QGELU_F16);
+    static constexpr bool kF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16 || kLn);
+    static constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_F32_LN);
+    static constexpr bool kStats = (EPI == EPI_BIAS_RESID_F32_LN);
+    static constexpr int kWarps = kF16 ? 16 : 8;
+    static constexpr int kThreads = 64 + 32 * kWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
+};
 
 template <int BLOCK_N>
 struct Gemm2Smem {
@@ -41,7 +56,7 @@ struct Gemm2Smem {
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
-    static constexpr int kStagingBytes = kGemm2EpiWarps * 32 * kStgLd * 4;
+    static constexpr int kStagingBytes = 32 * 1024;   // 16 warps x (32 rows x 64 B fp16) or 8 warps x (32 rows x 128 B fp32)
     static constexpr int kBarrierBytes = 256;
     static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /* alignment slack */;
     static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -117,34 +132,41 @@ __device__ __forceinline__ void umma_commit_cta2_mc(uint64_t* bar, uint16_t cta_
         : "memory");
 }
 
-// One 32-row x 32-column chunk of the accumulator leaves through a swizzled smem transpose so that
-// global accesses are 4 rows x 128 B (fp32) or 4 rows x 64 B (fp16) per warp instruction.
-// All global reads of the chunk (residual rows / position rows) are issued BEFORE the TMEM load and
-// the transpose so their latency overlaps them.  t_addr: TMEM address (lane quadrant + column) of the
-// chunk; m_base: global row of this warp's first row; col0: first global column of the chunk.
+// ---- fp32 epilogues (residual add, position add): transposed through shared memory ----
+// A warp's 32-row x 32-column chunk of the accumulator leaves through an XOR-swizzled smem transpose so
+// that global accesses are 4 rows x 128 B per warp instruction.  Lane layout after the transpose:
+// cq = lane & 7 is the 4-column group, rows r0 + 4 i (r0 = lane >> 3, i = 0..7).
+//
+// The residual / position rows of a chunk ("side" values) are loaded by gemm2_load_side one chunk AHEAD
+// of their use (across tiles too), so the HBM round trip overlaps the TMEM drain of the previous chunk.
 template <int EPI>
-__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32_t stg, uint32_t t_addr, int m_base, int col0,
-                                                     int lane, const float4 bias) {
-    const int cq = lane & 7;       // this lane's 4-column group
-    const int r0 = lane >> 3;      // rows r0, r0 + 4, ..., r0 + 28
-    const int col = col0 + 4 * cq;
-    float4 side[8];                // residual (EPI 2) or position-embedding (EPI 3) values
-    size_t orow[8];
+__device__ __forceinline__ void gemm2_load_side(const GemmParams& p, int m_base, int col0, int lane, float4 (&side)[8]) {
+    const int col = col0 + 4 * (lane & 7);
+    const int r0 = lane >> 3;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m_base + r0 + 4 * i;
         side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        orow[i] = static_cast<size_t>(m);
-        if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            if (m < p.m_valid) side[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
-        } else if constexpr (EPI == EPI_POS_F32) {
-            // patch row m of image b -> token row b * seq + 1 + patch, plus its position embedding
-            const int b = m / p.np;
-            const int pi = m - b * p.np;
-            orow[i] = static_cast<size_t>(b) * p.seq + 1 + pi;
+        if constexpr (EpiTraits<EPI>::kResid) {
+            if (m < p.m_valid && !(p.dbg_skip & 8)) side[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
+        } else {   // EPI_POS_F32: patch row m of image b carries position 1 + patch
+            const int pi = m % p.np;
             if (m < p.m_valid) side[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.ldo + col));
         }
     }
+}
+
+// t_addr: TMEM address (lane quadrant + column) of the chunk; m_base: global row of this warp's first
+// row; col0: first global column of the chunk.  s1 / s2 accumulate, per lane, the sum and the sum of
+// squares of the values written to rows r0 + 4 i (EPI_BIAS_RESID_F32_LN only).
+template <int EPI>
+__device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32_t stg, uint32_t t_addr, int m_base, int col0,
+                                                     int lane, const float4 bias, const float4 (&side)[8], float (&s1)[8],
+                                                     float (&s2)[8]) {
+    const int cq = lane & 7;
+    const int r0 = lane >> 3;
+    const int col = col0 + 4 * cq;
+    if (p.dbg_skip & 4) return;
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_addr, acc);
     tmem_ld_wait();
@@ -159,63 +181,111 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32
         const int r = r0 + 4 * i;
         const int m = m_base + r;
         float4 v = lds_v4(stg + r * (kStgLd * 4) + ((cq ^ (r & 7)) << 4));
-        if (m < p.m_valid) {
-            if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16) {
-                v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-                if constexpr (EPI == EPI_BIAS_QGELU_F16) {
-                    v.x = __fdividef(v.x, 1.0f + __expf(-1.702f * v.x));
-                    v.y = __fdividef(v.y, 1.0f + __expf(-1.702f * v.y));
-                    v.z = __fdividef(v.z, 1.0f + __expf(-1.702f * v.z));
-                    v.w = __fdividef(v.w, 1.0f + __expf(-1.702f * v.w));
-                }
-                *reinterpret_cast<uint2*>(static_cast<op16_t*>(p.out) + orow[i] * p.ldo + col) =
-                    make_uint2(pack_op16x2(v.x, v.y), pack_op16x2(v.z, v.w));
-            } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        if (m < p.m_valid && (!(p.dbg_skip & 1) || v.x == 123.456f)) {
+            if constexpr (EpiTraits<EPI>::kResid) {
                 v.x = side[i].x + (v.x + bias.x); v.y = side[i].y + (v.y + bias.y);
                 v.z = side[i].z + (v.z + bias.z); v.w = side[i].w + (v.w + bias.w);
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow[i] * p.ldo + col) = v;
-            } else {  // EPI_POS_F32
+                const size_t off = static_cast<size_t>(m) * p.ldo + col;
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
+                if constexpr (EpiTraits<EPI>::kStats) {
+                    *reinterpret_cast<uint2*>(p.out16 + off) = make_uint2(pack_op16x2(v.x, v.y), pack_op16x2(v.z, v.w));
+                    s1[i] += (v.x + v.y) + (v.z + v.w);
+                    s2[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                }
+            } else {  // EPI_POS_F32: patch row m of image b -> token row b * seq + 1 + patch
+                const int b = m / p.np;
+                const size_t orow = static_cast<size_t>(b) * p.seq + 1 + (m - b * p.np);
                 v.x += side[i].x; v.y += side[i].y; v.z += side[i].z; v.w += side[i].w;
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow[i] * p.ldo + col) = v;
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + col) = v;
             }
         }
     }
     __syncwarp();
 }
 
-// fp16-output epilogues (bias, bias + quick_gelu): the math runs on the TMEM registers (row per
-// thread, 32 independent columns -> deep MUFU pipelining), only the packed fp16 result (64 B per
-// row) goes through the staging transpose, and HBM sees 8 rows x 64 B per warp instruction.
+// ---- fp16-output epilogues (bias, LayerNorm fold, quick_gelu) ----
+// The math runs on the TMEM registers (row per thread, 32 independent columns -> deep MUFU pipelining),
+// only the packed fp16 result (64 B per row) goes through the staging transpose, and HBM sees
+// 8 rows x 64 B per warp instruction.  rstd / nmr (= -mu * rstd) are this thread's row statistics.
+// 2D tiled store shared -> global (bulk async group of the issuing thread); rows / columns outside the
+// tensor are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the staging tile of every committed store of this thread has been read (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int EPI>
-__device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, uint32_t stg, uint32_t t_addr, int m_base,
-                                                         int col0, int lane) {
-    static_assert(EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16, "fp16-output epilogues only");
+__device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, const CUtensorMap* tmap_out, uint32_t stg,
+                                                         uint32_t t_addr, int m_base, int col0, int lane, float rstd, float nmr) {
+    using T = EpiTraits<EPI>;
+    static_assert(T::kF16, "fp16-output epilogues only");
+    if (p.dbg_skip & 4) return;
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_addr, acc);
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform addresses: broadcast loads
-    float4 bias[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
-    tmem_ld_wait();
+    const float4* c4 = reinterpret_cast<const float4*>(p.colsum + col0);
     uint32_t pk[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float v0 = __uint_as_float(acc[4 * j + 0]) + bias[j].x;
-        float v1 = __uint_as_float(acc[4 * j + 1]) + bias[j].y;
-        float v2 = __uint_as_float(acc[4 * j + 2]) + bias[j].z;
-        float v3 = __uint_as_float(acc[4 * j + 3]) + bias[j].w;
-        if constexpr (EPI == EPI_BIAS_QGELU_F16) {
-            v0 = __fdividef(v0, 1.0f + __expf(-1.702f * v0));
-            v1 = __fdividef(v1, 1.0f + __expf(-1.702f * v1));
-            v2 = __fdividef(v2, 1.0f + __expf(-1.702f * v2));
-            v3 = __fdividef(v3, 1.0f + __expf(-1.702f * v3));
+    for (int h = 0; h < 2; ++h) {   // 16 columns at a time keeps the column vectors at 32 registers
+        float4 bias[4], cs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bias[j] = __ldg(b4 + 4 * h + j);
+            if constexpr (T::kLn) cs[j] = __ldg(c4 + 4 * h + j);
         }
-        pk[2 * j + 0] = pack_op16x2(v0, v1);
-        pk[2 * j + 1] = pack_op16x2(v2, v3);
+        if (h == 0) tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = 16 * h + 4 * j;
+            float v0, v1, v2, v3;
+            if constexpr (T::kLn) {
+                v0 = fmaf(rstd, __uint_as_float(acc[a + 0]), fmaf(nmr, cs[j].x, bias[j].x));
+                v1 = fmaf(rstd, __uint_as_float(acc[a + 1]), fmaf(nmr, cs[j].y, bias[j].y));
+                v2 = fmaf(rstd, __uint_as_float(acc[a + 2]), fmaf(nmr, cs[j].z, bias[j].z));
+                v3 = fmaf(rstd, __uint_as_float(acc[a + 3]), fmaf(nmr, cs[j].w, bias[j].w));
+            } else {
+                v0 = __uint_as_float(acc[a + 0]) + bias[j].x;
+                v1 = __uint_as_float(acc[a + 1]) + bias[j].y;
+                v2 = __uint_as_float(acc[a + 2]) + bias[j].z;
+                v3 = __uint_as_float(acc[a + 3]) + bias[j].w;
+            }
+            if constexpr (T::kGelu) {
+                v0 = quick_gelu(v0); v1 = quick_gelu(v1); v2 = quick_gelu(v2); v3 = quick_gelu(v3);
+            }
+            pk[8 * h + 2 * j + 0] = pack_op16x2(v0, v1);
+            pk[8 * h + 2 * j + 1] = pack_op16x2(v2, v3);
+        }
+    }
+    if (p.dbg_skip & 2) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x ^= pk[j];
+        if (x == 0x12345678u) *reinterpret_cast<uint32_t*>(p.out) = x;   // keeps the math alive
+        return;
     }
     // staging tile: 32 rows x 64 B; 16-byte slot s of row r lives at slot s ^ ((r >> 1) & 3)  (conflict-free both ways)
     const uint32_t srow = stg + lane * 64;
     const int sw = (lane >> 1) & 3;
+    if (p.tma_store) {
+        // the staging layout IS the TMA SWIZZLE_64B layout of a 32-row x 64-byte box: one bulk store per chunk
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+            sts_v4u(srow + ((s4 ^ sw) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmap_out, stg, col0, m_base);
+            tma_store_commit();
+        }
+        return;
+    }
 #pragma unroll
     for (int s4 = 0; s4 < 4; ++s4)
         sts_v4u(srow + ((s4 ^ sw) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
@@ -227,29 +297,26 @@ __device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, ui
         const int r = r0 + 8 * i;
         const int m = m_base + r;
         const uint4 v = lds_v4u(stg + r * 64 + ((slot ^ ((r >> 1) & 3)) << 4));
-        if (m < p.m_valid)
+        if (m < p.m_valid && (!(p.dbg_skip & 1) || v.x == 0x12345678u))
             *reinterpret_cast<uint4*>(static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col0 + slot * 8) = v;
     }
     __syncwarp();
 }
 
-// p.m_tiles counts 256-row pair tiles.  PAIRS = 1: cluster of 2 CTAs (one pair).  PAIRS = 2: cluster of
-// 4 CTAs = two pairs working on vertically adjacent 256-row tiles of the SAME n-block; every CTA
-// fetches only a QUARTER of the W tile and multicasts it to its twin in the other pair, which cuts the
-// L2 -> SM operand traffic (the measured limiter of the k-loop) from 64 KB to 48 KB per pair k-block.
-// Launched with cudaLaunchKernelEx + cluster dimension 2 * PAIRS.
-template <int BLOCK_N, int EPI, int PAIRS>
-__global__ void __launch_bounds__(kGemm2Threads, 1)
+// p.m_tiles counts 256-row pair tiles.  Launched with cudaLaunchKernelEx + cluster dimension 2.
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(EpiTraits<EPI>::kThreads, 1)
 gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const GemmParams p) {
+                        const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     using L = Gemm2Smem<BLOCK_N>;
+    using T = EpiTraits<EPI>;
     constexpr int kStages = L::kStages;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
     static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* staging = reinterpret_cast<float*>(smem + kStages * L::kStageBytes);
+    uint8_t* staging = smem + kStages * L::kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes + L::kStagingBytes);
     uint64_t* full_bar = bars;                      // [kStages]
     uint64_t* empty_bar = bars + kStages;           // [kStages]
@@ -259,28 +326,22 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    static_assert(PAIRS == 1 || PAIRS == 2, "PAIRS");
-    const uint32_t crank = cluster_ctarank();          // 0 .. 2 * PAIRS - 1
-    const uint32_t rank = crank & 1;                   // rank inside the CTA pair (0 = leader)
-    const uint32_t pair = crank >> 1;
-    const uint32_t leader = crank & ~1u;               // cluster rank of this pair's leader
-    const int cluster_id = blockIdx.x / (2 * PAIRS);
-    const int num_clusters = gridDim.x / (2 * PAIRS);
-    const int m_ctiles = (p.m_tiles + PAIRS - 1) / PAIRS;      // cluster tiles along M
-    const int num_tiles = m_ctiles * p.n_tiles;
-    constexpr uint16_t kAllMask = (1u << (2 * PAIRS)) - 1;
-    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
+    const uint32_t rank = cluster_ctarank();           // rank inside the CTA pair (0 = leader)
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_tiles = p.m_tiles * p.n_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (p.tma_store) tma_prefetch_desc(&tmap_out);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], PAIRS);   // every pair that reads this stage (all write into it) must release it
+            mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 2 * kGemm2EpiWarps);
+            mbar_init(&tmem_empty[i], 2 * T::kWarps);
         }
         fence_barrier_init();
     }
@@ -294,35 +355,29 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     if (warp == 0) {
         if (elect_one()) {
-            // ===== TMA producer (every CTA): own A rows, own share of W; bytes land on the pair leader's full barrier =====
+            // ===== TMA producer (both CTAs): own A rows, own half of W; bytes land on the leader's full barrier =====
             int stage = 0;
             uint32_t phase = 0;
-            constexpr int kWRows = BLOCK_N / (2 * PAIRS);     // W rows this CTA fetches per k-block
-            const uint16_t w_mask = static_cast<uint16_t>((1u << rank) | (PAIRS == 2 ? (1u << (rank + 2)) : 0u));
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int mc = tile / p.n_tiles;
-                const int n_blk = tile - mc * p.n_tiles;
-                const int m_blk = mc * PAIRS + static_cast<int>(pair);
+                const int m_blk = tile / p.n_tiles;
+                const int n_blk = tile - m_blk * p.n_tiles;
                 const int a_row = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM;
-                const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) + static_cast<int>(pair) * kWRows;
+                const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
-                    uint8_t* sb = sa + L::kABytes + static_cast<int>(pair) * (kWRows * kGemmBlockK * 2);
+                    uint8_t* sb = sa + L::kABytes;
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-                    const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), leader);
+                    const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
                     tma_load_2d_cta2(sa, &tmap_a, bar, kb * kGemmBlockK, a_row);
-                    if constexpr (PAIRS == 1)
-                        tma_load_2d_cta2(sb, &tmap_b, bar, kb * kGemmBlockK, b_row);
-                    else
-                        tma_load_2d_cta2_mc(sb, &tmap_b, bar, kb * kGemmBlockK, b_row, w_mask);
+                    tma_load_2d_cta2(sb, &tmap_b, bar, kb * kGemmBlockK, b_row);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (rank == 0 && elect_one()) {
-            // ===== MMA issuer (pair leaders only) =====
+            // ===== MMA issuer (pair leader only) =====
             constexpr uint32_t idesc = make_idesc_f16(kGemm2TileM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -341,10 +396,10 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 16; ++k)
                         umma_f16_cta2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_cta2_mc(&empty_bar[stage], kAllMask);   // the stage is written by CTAs of every pair
+                    umma_commit_cta2_mc(&empty_bar[stage], 3);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_cta2_mc(&tmem_full[as], pair_mask);
+                umma_commit_cta2_mc(&tmem_full[as], 3);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -352,46 +407,131 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         // ===== epilogue warps (both CTAs): TMEM -> registers -> smem transpose -> coalesced HBM =====
         const int ew = warp - 2;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;           // which half of the tile's columns this warp drains
-        constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
-        const uint32_t stg = smem_u32(staging + ew * 32 * kStgLd);   // shared-space address of this warp's staging tile
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int mc = tile / p.n_tiles;
-            const int n_blk = tile - mc * p.n_tiles;
-            const int m_blk = mc * PAIRS + static_cast<int>(pair);
-            const int m_base = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
-            const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
-            float4 bias[kChunks];
+        if constexpr (T::kF16) {
+            const int slice = ew >> 2;                  // which quarter of the tile's columns this warp drains
+            constexpr int kSliceCols = BLOCK_N / 4;
+            constexpr int kChunks = kSliceCols / 32;    // 32-column chunks per warp
+            const uint32_t stg = smem_u32(staging + ew * 2048);
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = tile / p.n_tiles;
+                const int n_blk = tile - m_blk * p.n_tiles;
+                const int m_base = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
+                const int col_base = n_blk * BLOCK_N + slice * kSliceCols;
+                float rstd = 1.f, nmr = 0.f;
+                if constexpr (T::kLn) {
+                    // row statistics from the partial sums the producing epilogue (or embed_finish) left
+                    // (all loads are issued before the first use: a load-add loop would serialise the L2 round trips)
+                    const int m = m_base + lane;
+                    float2 t[kMaxStatsParts];
 #pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                bias[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (EPI == EPI_BIAS_RESID_F32)
-                    bias[c] = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + c * 32 + 4 * (lane & 7)));
+                    for (int q = 0; q < kMaxStatsParts; ++q) {
+                        t[q] = make_float2(0.f, 0.f);
+                        if (q < p.stats_parts && m < p.m_valid) t[q] = __ldg(p.stats_in + static_cast<size_t>(q) * p.stats_ld + m);
+                    }
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < kMaxStatsParts; ++q) {
+                        s1 += t[q].x;
+                        s2 += t[q].y;
+                    }
+                    const float mu = s1 * p.inv_k;
+                    rstd = rsqrtf(fmaxf(s2 * p.inv_k - mu * mu, 0.f) + p.eps);
+                    nmr = -mu * rstd;
+                }
+                mbar_wait(&tmem_full[as], aphase);
+                tcgen05_fence_after();
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + slice * kSliceCols;
+                if (m_base < p.m_valid) {
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c)
+                        gemm2_epilogue_chunk_f16<EPI>(p, &tmap_out, stg, t_row + c * 32, m_base, col_base + c * 32, lane, rstd, nmr);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (rank == 0) mbar_arrive(&tmem_empty[as]);
+                    else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
             }
-            mbar_wait(&tmem_full[as], aphase);
-            tcgen05_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
-            if (m_base < p.m_valid) {
+        } else {
+            const int half = ew >> 2;               // which half of the tile's columns this warp drains
+            constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
+            static_assert(kChunks % 2 == 0, "the side-value double buffer alternates per chunk");
+            const uint32_t stg = smem_u32(staging + ew * 4096);
+            auto tile_rows = [&](int tile, int& n_blk) {
+                const int m_blk = tile / p.n_tiles;
+                n_blk = tile - m_blk * p.n_tiles;
+                return m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
+            };
+            float4 side[2][8];
+            int tile = cluster_id;
+            if (tile < num_tiles) {
+                int n_blk;
+                const int m_base = tile_rows(tile, n_blk);
+                gemm2_load_side<EPI>(p, m_base, n_blk * BLOCK_N + half * (BLOCK_N / 2), lane, side[0]);
+            }
+            for (; tile < num_tiles; tile += num_clusters) {
+                int n_blk, n_blk_next = 0;
+                const int m_base = tile_rows(tile, n_blk);
+                const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
+                const bool has_next = tile + num_clusters < num_tiles;
+                const int m_base_next = has_next ? tile_rows(tile + num_clusters, n_blk_next) : 0;
+                float s1[8], s2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+                mbar_wait(&tmem_full[as], aphase);
+                tcgen05_fence_after();
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
-                    if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16)
-                        gemm2_epilogue_chunk_f16<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane);
-                    else
-                        gemm2_epilogue_chunk<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias[c]);
+                    if (c + 1 < kChunks)
+                        gemm2_load_side<EPI>(p, m_base, col_base + (c + 1) * 32, lane, side[(c + 1) & 1]);
+                    else if (has_next)
+                        gemm2_load_side<EPI>(p, m_base_next, n_blk_next * BLOCK_N + half * (BLOCK_N / 2), lane, side[0]);
+                    if (m_base < p.m_valid) {
+                        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if constexpr (T::kResid)
+                            bias = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + c * 32 + 4 * (lane & 7)));
+                        gemm2_epilogue_chunk<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias, side[c & 1], s1, s2);
+                    }
                 }
+                if constexpr (T::kStats) {
+                    // the 8 lanes that share a row (cq = 0..7) fold their partial sums; lane cq == 0 writes them
+                    // (transposing butterfly: 7 shuffles per quantity; lane cq ends up with the totals of row r0 + 4 cq)
+                    if (m_base < p.m_valid) {
+#pragma unroll
+                        for (int w = 4; w >= 1; w >>= 1) {
+                            const bool up = (lane & w) != 0;
+#pragma unroll
+                            for (int i = 0; i < w; ++i) {
+                                const float a1 = __shfl_xor_sync(0xffffffffu, up ? s1[i] : s1[i + w], w);
+                                const float a2 = __shfl_xor_sync(0xffffffffu, up ? s2[i] : s2[i + w], w);
+                                s1[i] = (up ? s1[i + w] : s1[i]) + a1;
+                                s2[i] = (up ? s2[i + w] : s2[i]) + a2;
+                            }
+                        }
+                        const int m = m_base + (lane >> 3) + 4 * (lane & 7);
+                        if (m < p.m_valid)
+                            p.stats_out[static_cast<size_t>(n_blk * 2 + half) * p.stats_ld + m] = make_float2(s1[0], s2[0]);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (rank == 0) mbar_arrive(&tmem_empty[as]);
+                    else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (rank == 0) mbar_arrive(&tmem_empty[as]);
-                else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), leader));
-            }
-            if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
 
+    if constexpr (T::kF16) {
+        if (warp >= 2 && lane == 0 && p.tma_store) tma_store_wait_all();   // bulk stores must have completed before the CTA exits
+    }
     __syncwarp();
     tcgen05_fence_before();
     cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still signal its barriers

@@ -97,12 +97,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // Finish the embeddings after the patch GEMM has written  patch . W + pos  into the patch rows of x:
 //   row b*S      <- class_embedding + pos[0]                    (HF:212-213,217)
 //   every row    <- pre_layrnorm(row)                            (HF:677)   -> x   (fp32 residual stream)
-//   and          <- layer_norm1 of layer 0 applied on top        (HF:371)   -> xn  (fp16 GEMM operand)
+// plus what the LayerNorm-folded q/k/v projection of layer 0 reads (gemm_tcgen05.cuh): the fp16 copy of
+// the row (xh) and its (sum, sum of squares) as part 0 of the row statistics.
 template <int VEC>
 __global__ void __launch_bounds__(kRowThreads)
-embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xn, const float* __restrict__ cls,
-                    const float* __restrict__ pos, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
-                    const float* __restrict__ ln1_g, const float* __restrict__ ln1_b, int M, int S, float eps) {
+embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, float2* __restrict__ stats, const float* __restrict__ cls,
+                    const float* __restrict__ pos, const float* __restrict__ pre_g, const float* __restrict__ pre_b, int M, int S,
+                    float eps) {
     constexpr int D = 128 * VEC;
     pdl_launch_dependents();
     pdl_wait();
@@ -118,9 +119,49 @@ embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xn, const float*
     }
     r.layernorm(pre_g, pre_b, eps, lane);
     r.store_f32(x + static_cast<size_t>(row) * D, lane);
-    if (xn != nullptr) {
-        r.layernorm(ln1_g, ln1_b, eps, lane);
-        r.store_f16(xn + static_cast<size_t>(row) * D, lane);
+    if (xh != nullptr) {
+        r.store_f16(xh + static_cast<size_t>(row) * D, lane);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            s1 += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+            s2 += (r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) stats[row] = make_float2(s1, s2);
+    }
+}
+
+// LayerNorm fold of one projection (gemm_tcgen05.cuh), one warp per output row n of W [N, K]:
+//   w16[n, k] = fp16(gamma[k] * W[n, k]),  c[n] = sum_k w16[n, k] (the ROUNDED operand, so that a constant
+//   row cancels exactly),  d[n] = bias[n] + sum_k beta[k] * W[n, k]
+__global__ void __launch_bounds__(256)
+fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ bias, op16_t* __restrict__ w16, float* __restrict__ c, float* __restrict__ d,
+                      int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float* wr = w + static_cast<size_t>(n) * K;
+    op16_t* o = w16 + static_cast<size_t>(n) * K;
+    float sc = 0.f, sd = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float v = wr[k];
+        const op16_t q = to_op16(gamma[k] * v);
+        o[k] = q;
+#ifdef MCM_OP_BF16
+        sc += __bfloat162float(q);
+#else
+        sc += __half2float(q);
+#endif
+        sd = fmaf(beta[k], v, sd);
+    }
+    sc = warp_sum(sc);
+    sd = warp_sum(sd);
+    if (lane == 0) {
+        c[n] = sc;
+        d[n] = bias[n] + sd;
     }
 }
 

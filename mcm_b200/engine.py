@@ -179,6 +179,39 @@ class McmEngine:
                                            _ptr(resid), _ptr(out), M, N, K, int(epi), self._stream()))
         return out
 
+    def dbg_fold_ln(self, w, gamma, beta, bias):
+        """LayerNorm fold of one projection: (w16 = fp16(gamma o W), c, d); see csrc/gemm_tcgen05.cuh."""
+        N, K = w.shape
+        w16 = torch.empty((N, K), dtype=torch.float16, device=self.device)
+        c = torch.empty((N,), dtype=torch.float32, device=self.device)
+        d = torch.empty((N,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_dbg_fold_ln(self._h, _ptr(w.contiguous()), _ptr(gamma), _ptr(beta), _ptr(bias), _ptr(w16),
+                                              _ptr(c), _ptr(d), N, K, self._stream()))
+        return w16, c, d
+
+    def dbg_gemm_resid_ln(self, a, w, bias, resid):
+        """out = resid + A @ W^T + bias (fp32), its fp16 copy and the partial row statistics [parts, M, 2]."""
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        out16 = torch.empty((M, N), dtype=torch.float16, device=self.device)
+        stats = torch.zeros((N // 64, M, 2), dtype=torch.float32, device=self.device)
+        parts = C.c_int32(0)
+        self._check(self._lib.mcm_dbg_gemm_resid_ln(self._h, _ptr(a.contiguous()), _ptr(w.contiguous()), _ptr(bias),
+                                                    _ptr(resid.contiguous()), _ptr(out), _ptr(out16), _ptr(stats), M, N, K,
+                                                    C.byref(parts), self._stream()))
+        return out, out16, stats[:parts.value]
+
+    def dbg_gemm_ln(self, a, w16, d, c, stats, row_len: int, gelu: bool = False):
+        """[quick_gelu](LayerNorm(rows) @ W^T + b) through the folded projection; stats: [parts, M, 2] fp32."""
+        M, K = a.shape
+        N = w16.shape[0]
+        out = torch.empty((M, N), dtype=torch.float16, device=self.device)
+        stats = stats.contiguous()
+        self._check(self._lib.mcm_dbg_gemm_ln(self._h, _ptr(a.contiguous()), _ptr(w16.contiguous()), _ptr(d), _ptr(c), _ptr(stats),
+                                              stats.shape[0], int(row_len), _ptr(out), M, N, K, 1 if gelu else 0, self._stream()))
+        return out
+
     def dbg_layernorm(self, x, gamma, beta, eps: float = 1e-5, out_f16: bool = True):
         M, D = x.shape
         out = torch.empty((M, D), dtype=torch.float16 if out_f16 else torch.float32, device=self.device)

@@ -65,3 +65,53 @@ def test_gemm_in_place_residual(engine_factory):
     _lib.check(rc, eng._h)
     torch.cuda.synchronize()
     assert (x - ref).abs().max().item() <= 2e-3
+
+
+# ---- LayerNorm folded into the projection (csrc/gemm_tcgen05.cuh): producer epilogue writes the fp16
+#      copy + partial row statistics, consumer epilogue applies mu / rstd; HF:371-372,380-381 ----
+LN_SHAPES = [
+    (256, 256, 128, 256),     # M, D (= N of the producer, K of the consumer), K of the producer, N of the consumer
+    (200, 128, 64, 384),      # ragged M, BLOCK_N = 128 on both sides
+    (1576, 768, 768, 2304),   # out_proj -> q/k/v of ViT-B/16
+    (197 * 160, 768, 128, 256),   # more tiles than clusters: residual prefetch across tiles
+]
+
+
+@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("M,D,K1,N2", LN_SHAPES)
+def test_gemm_layernorm_fold_matches_torch(engine_factory, M, D, K1, N2, gelu):
+    eng, _, _ = engine_factory("tiny", 5, 8)
+    g = torch.Generator(device="cuda").manual_seed(M + D + K1 + N2)
+    a = torch.randn(M, K1, device="cuda", generator=g).to(torch.float16)
+    w_o = (torch.randn(D, K1, device="cuda", generator=g) * K1 ** -0.5).to(torch.float16)
+    b_o = torch.randn(D, device="cuda", generator=g)
+    # a residual stream with a per-row offset and spread, so that mu and rstd matter
+    resid = torch.randn(M, D, device="cuda", generator=g) * (0.5 + torch.rand(M, 1, device="cuda", generator=g) * 3) \
+        + torch.randn(M, 1, device="cuda", generator=g)
+    gamma = 1.0 + 0.2 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(D, device="cuda", generator=g)
+    w_p = torch.randn(N2, D, device="cuda", generator=g) * D ** -0.5
+    b_p = torch.randn(N2, device="cuda", generator=g)
+
+    x, x16, stats = eng.dbg_gemm_resid_ln(a, w_o, b_o, resid)
+    w16, c, d = eng.dbg_fold_ln(w_p, gamma, beta, b_p)
+    y = eng.dbg_gemm_ln(x16, w16, d, c, stats, D, gelu=gelu)
+    torch.cuda.synchronize()
+
+    x_ref = _ref(a, w_o, b_o, resid, 2)
+    assert (x - x_ref).abs().max().item() <= 2e-3
+    assert torch.equal(x16, x.to(torch.float16))                      # the fp16 copy is the rounded fp32 result
+    s = stats.sum(0)
+    assert torch.allclose(s[:, 0], x.sum(1), rtol=1e-4, atol=1e-2)    # partial sums add up to the row statistics
+    assert torch.allclose(s[:, 1], (x * x).sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(c, w16.float().sum(1), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(d, b_p + w_p @ beta, rtol=1e-4, atol=1e-4)
+
+    xn = torch.nn.functional.layer_norm(x_ref, (D,), gamma, beta, eng.cfg.eps)
+    y_ref = xn @ w_p.t() + b_p
+    if gelu:
+        y_ref = y_ref * torch.sigmoid(1.702 * y_ref)
+    # same error budget as a projection of the fp16-rounded LayerNorm output (operand rounding 2^-11)
+    err = (y.float() - y_ref).abs().max().item()
+    rel = ((y.float() - y_ref).abs() / (y_ref.abs() + 1.0)).max().item()
+    assert err <= 6e-2 and rel <= 1e-2, f"M={M} D={D} N={N2}: max|d|={err} rel={rel}"
