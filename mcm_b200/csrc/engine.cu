@@ -171,24 +171,28 @@ struct ProfScope {
             return fail(h, MCM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-// fp16 [rows, cols] output of a GEMM epilogue: 32-row x 32-column boxes (64 B inner dimension, 64-byte swizzle =
-// the layout of the epilogue's staging tile)
-int make_tmap_out16(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+// Row-major [rows, cols] output (or in-place residual) of a GEMM epilogue: 32-row x box_cols boxes whose smem image
+// is the epilogue's staging tile (inner dimension 64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B).
+int make_tmap_epi(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, bool f32, uint32_t box_cols) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    const uint32_t esz = f32 ? 4 : sizeof(op16_t);
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {cols * sizeof(op16_t)};
-    cuuint32_t box[2] = {32, 32};
+    cuuint64_t gstr[1] = {cols * esz};
+    cuuint32_t box[2] = {box_cols, 32};
     cuuint32_t estr[2] = {1, 1};
 #ifdef MCM_OP_BF16
     constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 #else
     constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 #endif
-    CUresult r = enc(m, kOpType, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const uint32_t inner = box_cols * esz;
+    if (inner != 64 && inner != 128) return fail(h, MCM_EINVAL, "epilogue box of %u bytes per row unsupported", inner);
+    CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : kOpType, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
-        return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled (output) failed (%d) rows=%llu cols=%llu", (int)r,
+        return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled (epilogue) failed (%d) rows=%llu cols=%llu", (int)r,
                     (unsigned long long)rows, (unsigned long long)cols);
     return MCM_OK;
 }
@@ -250,17 +254,17 @@ inline int cuda_rc(McmHandle* h, cudaError_t e) {
 inline int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
 template <int BN, int EPI>
-int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
-                   cudaStream_t st) {
+int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tout16,
+                   const GemmParams& p, cudaStream_t st) {
     static bool attr_done = false;   // per instantiation; one device per process in practice
     auto kern = gemm_f16_tn_cta2_kernel<BN, EPI>;
     if (!attr_done) {
-        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
+        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN, EPI>::kTotal));
         attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int clusters = std::min(tiles, h->num_sms / 2);   // persistent: one CTA pair per TPC
-    MCM_CUDA(h, launch_k(kern, dim3(2 * clusters), dim3(EpiTraits<EPI>::kThreads), Gemm2Smem<BN>::kTotal, st, 2, ta, tb, tout, p));
+    MCM_CUDA(h, launch_k(kern, dim3(2 * clusters), dim3(EpiTraits<EPI>::kThreads), Gemm2Smem<BN, EPI>::kTotal, st, 2, ta, tb, tout, tout16, p));
     h->launches++;
     return MCM_OK;
 }
@@ -304,21 +308,55 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     p.eps = h->cfg.eps;
     p.out16 = ln.out16;
     p.stats_out = ln.stats_out;
-    // fp16 outputs leave through TMA bulk stores (measured 6-9 % faster on the K = 768 projections than LSU stores of the
-    // same staging tile: the stores share the SM <-> L2 path with the operand loads); MCM_GEMM_TMA_STORE=0 is the A/B switch
-    static const bool tma_store = [] { const char* e = getenv("MCM_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
-    CUtensorMap tout = ta;   // placeholder for the kinds that do not store through TMA
+    // Epilogue traffic that goes through TMA (fp16 outputs; the residual epilogue of EPI_BIAS_RESID_F32_LN_TMA) needs
+    // tensor maps over the caller's buffers with exactly M rows, so that the TMA unit clips the last tile.
+    CUtensorMap tout = ta, tout16 = ta;   // placeholders for the kinds that do not use them
     const bool f16_out = epi == EPI_BIAS_F16 || epi == EPI_BIAS_QGELU_F16 || epi == EPI_LN_F16 || epi == EPI_LN_QGELU_F16;
-    p.tma_store = (tma_store && f16_out) ? 1 : 0;
-    if (p.tma_store) {
-        int rc = make_tmap_out16(h, &tout, out, M, N);   // exactly M rows: the TMA unit clips the last tile
-        if (rc) return rc;
+    if (epi == EPI_BIAS_RESID_F32_LN) {
+        // the LSU epilogue stays for long-K GEMMs (its time hides behind the main loop and it leaves 6 ring stages);
+        // MCM_GEMM_RESID_TMA=0 / 1 forces one or the other (A/B runs)
+        static const int force = [] { const char* e = getenv("MCM_GEMM_RESID_TMA"); return e ? atoi(e) : -1; }();
+        const bool use_tma = resid == out && (force >= 0 ? force != 0 : K <= 1024);
+        if (use_tma) epi = EPI_BIAS_RESID_F32_LN_TMA;
     }
+    if (f16_out) {
+        int rc = make_tmap_epi(h, &tout, out, M, N, false, bn / 4);
+        if (rc) return rc;
+    } else if (epi == EPI_BIAS_RESID_F32_LN_TMA) {
+        int rc = make_tmap_epi(h, &tout, out, M, N, true, 32);
+        if (rc) return rc;
+        if ((rc = make_tmap_epi(h, &tout16, ln.out16, M, N, false, 32))) return rc;
+    }
+    p.trace = nullptr;
+#ifdef MCM_GEMM_TRACE
+    {   // debug build: per-launch cycle counters, printed after the launch (synchronises!)
+        static long long* tr = nullptr;
+        if (!tr) cudaMalloc(&tr, 8 * sizeof(long long));
+        cudaMemsetAsync(tr, 0, 8 * sizeof(long long), st);
+        p.trace = tr;
+    }
+#endif
     static const int dbg_skip = [] { const char* e = getenv("MCM_GEMM_DBG_SKIP"); return e ? atoi(e) : 0; }();
     p.dbg_skip = dbg_skip;
     ProfScope prof(h, prof_kind, st);
+#ifdef MCM_GEMM_TRACE
+    struct TraceDump {
+        McmHandle* h; long long* tr; cudaStream_t st; int M, N, K, epi;
+        ~TraceDump() {
+            static const bool on = getenv("MCM_GEMM_TRACE_PRINT") != nullptr;
+            if (!on) return;
+            long long t[8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(t, tr, sizeof t, cudaMemcpyDeviceToHost);
+            const double nc = h->num_sms / 2, nt = (double)t[3];
+            printf("GEMM_TRACE M=%d N=%d K=%d epi=%d: per tile: mma_total %.0f  wait_acc %.0f  wait_data %.0f | epi_wait %.0f epi_busy %.0f (cycles; %g tiles, %g clusters)\n",
+                   M, N, K, epi, t[2] / nt, t[0] / nt, t[1] / nt, t[4] / nt, t[5] / nt, nt, nc);
+            fflush(stdout);
+        }
+    } trace_dump{h, p.trace, st, M, N, K, epi};
+#endif
 #define MCM_GEMM_CASE(E)                                                     \
-    if (epi == E) return bn == 256 ? launch_gemm2_t<256, E>(h, ta, tb, tout, p, st) : launch_gemm2_t<128, E>(h, ta, tb, tout, p, st);
+    if (epi == E) return bn == 256 ? launch_gemm2_t<256, E>(h, ta, tb, tout, tout16, p, st) : launch_gemm2_t<128, E>(h, ta, tb, tout, tout16, p, st);
     MCM_GEMM_CASE(EPI_BIAS_F16)
     MCM_GEMM_CASE(EPI_BIAS_QGELU_F16)
     MCM_GEMM_CASE(EPI_BIAS_RESID_F32)
@@ -326,6 +364,7 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     MCM_GEMM_CASE(EPI_LN_F16)
     MCM_GEMM_CASE(EPI_LN_QGELU_F16)
     MCM_GEMM_CASE(EPI_BIAS_RESID_F32_LN)
+    MCM_GEMM_CASE(EPI_BIAS_RESID_F32_LN_TMA)
 #undef MCM_GEMM_CASE
     return fail(h, MCM_EINVAL, "unknown GEMM epilogue %d", epi);
 }

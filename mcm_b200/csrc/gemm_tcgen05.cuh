@@ -27,7 +27,8 @@ enum GemmEpilogue : int {
     EPI_LN_F16 = 4,            // out_f16 = rstd * acc - rstd * mu * c + d            (layer_norm1 folded into q/k/v)
     EPI_LN_QGELU_F16 = 5,      // out_f16 = quick_gelu(the same)                      (layer_norm2 folded into fc1)
     EPI_BIAS_RESID_F32_LN = 6, // EPI_BIAS_RESID_F32 + fp16 copy of the result + partial row statistics
-    EPI_KINDS = 7,
+    EPI_BIAS_RESID_F32_LN_TMA = 7,   // the same through TMA loads / stores (the tensor maps carry resid == out and out16)
+    EPI_KINDS = 8,
 };
 
 struct GemmParams {
@@ -51,7 +52,7 @@ struct GemmParams {
     float eps;
     op16_t* out16;           // EPI_BIAS_RESID_F32_LN: fp16 copy of out (the next projection's A operand)
     float2* stats_out;       // EPI_BIAS_RESID_F32_LN: [2 * n_tiles][stats_ld]
-    int tma_store;           // fp16-output epilogues: 1 = the chunks leave through TMA bulk stores (tmap_out), 0 = LSU stores
+    long long* trace;        // -DMCM_GEMM_TRACE builds: [8] cycle counters summed over CTAs (see tools/gemm_trace.py)
     int dbg_skip;            // timing experiments only (env MCM_GEMM_DBG_SKIP): 1 no global stores, 2 no staging either,
                              // 4 no TMEM drain at all, 8 no residual loads
 };
@@ -59,6 +60,20 @@ struct GemmParams {
 constexpr int kGemmBlockM = 128;   // rows per CTA (256 per CTA pair)
 constexpr int kGemmBlockK = 64;    // 64 fp16 = one 128-byte swizzle row
 
-__device__ __forceinline__ float quick_gelu(float v) { return __fdividef(v, 1.0f + __expf(-1.702f * v)); }
+// quick_gelu(v) = v * sigmoid(1.702 v)  (HF activations.py:117-123).
+// Default: one MUFU op per element through  sigmoid(z) = 0.5 + 0.5 tanh(z / 2)  (tanh.approx.f32, relative error
+// 2^-11: the absolute error stays below half an fp16 ulp of |v|, i.e. below the rounding of the fp16 output itself).
+// The fc1 epilogue is MUFU-bound with the two-op form (ex2 + rcp): 7.5 k cycles per 256 x 256 tile against a
+// 6.1 k-cycle main loop.  -DMCM_GELU_EXACT restores ex2 + rcp (A/B builds).
+__device__ __forceinline__ float quick_gelu(float v) {
+#ifdef MCM_GELU_EXACT
+    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+#else
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
+    const float h = 0.5f * v;
+    return fmaf(h, t, h);
+#endif
+}
 
 }  // namespace mcm

@@ -31,6 +31,8 @@
 namespace mcm {
 
 constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
+constexpr int kResidBufs = 2;        // TMA residual epilogue: residual chunks in flight per warp
+constexpr int kResidWarpBytes = kResidBufs * 4096 + 2048;   // + the fp16 staging tile
 constexpr int kMaxStatsParts = 8;    // LayerNorm fold: partial row statistics per row (width <= 1024: 2 per 256-column tile)
 constexpr int kStgLd = 32;           // fp32 staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
 
@@ -45,22 +47,31 @@ struct EpiTraits {
     static constexpr bool kGelu = (EPI == EPI_BIAS_QGELU_F16 || EPI == EPI_LN_QGELU_F16);
     static constexpr bool kF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16 || kLn);
     static constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_F32_LN);
+    static constexpr bool kTmaResid = (EPI == EPI_BIAS_RESID_F32_LN_TMA);   // residual epilogue through TMA loads / stores
     static constexpr bool kStats = (EPI == EPI_BIAS_RESID_F32_LN);
     static constexpr int kWarps = kF16 ? 16 : 8;
     static constexpr int kThreads = 64 + 32 * kWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 };
 
-template <int BLOCK_N>
+// Shared memory: operand ring + epilogue staging + barriers.  What the epilogue stages decides how many
+// ring stages are left of the 227 KB:
+//   fp16 outputs          16 warps x (32 rows x 128 B) = 64 KB : one TMA bulk store per warp and tile
+//   fp32, LSU             8 warps x (32 rows x 128 B)  = 32 KB : transpose tile (EPI_BIAS_RESID_F32, EPI_POS_F32, ..._LN)
+//   fp32 + fp16, TMA      8 warps x (2 x 4 KB residual in / fp32 out + 2 KB fp16 out) = 80 KB  (EPI_BIAS_RESID_F32_LN_TMA)
+template <int BLOCK_N, int EPI>
 struct Gemm2Smem {
+    using T = EpiTraits<EPI>;
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
-    static constexpr int kStagingBytes = 32 * 1024;   // 16 warps x (32 rows x 64 B fp16) or 8 warps x (32 rows x 128 B fp32)
-    static constexpr int kBarrierBytes = 256;
-    static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /* alignment slack */;
+    static constexpr int kStagingBytes = T::kF16 ? 16 * (BLOCK_N / 4) * 64 : T::kTmaResid ? 8 * kResidWarpBytes : 32 * 1024;
+    static constexpr int kBarrierBytes = 512;
+    static constexpr int kBudget = 232448 - 1024 /* alignment slack */ - kBarrierBytes - kStagingBytes;
+    static constexpr int kStages = (kBudget / kStageBytes) < 8 ? (kBudget / kStageBytes) : 8;
+    static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+    static_assert(kStages >= 3, "too few operand stages");
     static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
-    static_assert((2 * kStages + 4) * 8 + 4 <= kBarrierBytes, "barrier area too small");
+    static_assert((2 * kStages + 4 + 16) * 8 + 4 <= kBarrierBytes, "barrier area too small");
 };
 
 // ---- cluster / 2-CTA PTX ----
@@ -219,17 +230,18 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// TMEM chunk (32 rows x 32 columns) -> bias / LayerNorm fold / quick_gelu -> 16 packed fp16 pairs of this thread's row.
+// release_bar != 0 (last chunk of the tile): arrive on that cluster-space tmem_empty barrier as soon as the
+// accumulator values sit in registers, so the next-but-one tile's MMAs need not wait for the math and the stores.
 template <int EPI>
-__device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, const CUtensorMap* tmap_out, uint32_t stg,
-                                                         uint32_t t_addr, int m_base, int col0, int lane, float rstd, float nmr) {
+__device__ __forceinline__ void gemm2_f16_chunk_math(const GemmParams& p, uint32_t t_addr, int col0, int lane, float rstd, float nmr,
+                                                     uint32_t release_bar, uint32_t (&pk)[16]) {
     using T = EpiTraits<EPI>;
     static_assert(T::kF16, "fp16-output epilogues only");
-    if (p.dbg_skip & 4) return;
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_addr, acc);
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform addresses: broadcast loads
     const float4* c4 = reinterpret_cast<const float4*>(p.colsum + col0);
-    uint32_t pk[16];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {   // 16 columns at a time keeps the column vectors at 32 registers
         float4 bias[4], cs[4];
@@ -238,7 +250,14 @@ __device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, co
             bias[j] = __ldg(b4 + 4 * h + j);
             if constexpr (T::kLn) cs[j] = __ldg(c4 + 4 * h + j);
         }
-        if (h == 0) tmem_ld_wait();
+        if (h == 0) {
+            tmem_ld_wait();
+            if (release_bar) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(release_bar);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int a = 16 * h + 4 * j;
@@ -261,54 +280,73 @@ __device__ __forceinline__ void gemm2_epilogue_chunk_f16(const GemmParams& p, co
             pk[8 * h + 2 * j + 1] = pack_op16x2(v2, v3);
         }
     }
-    if (p.dbg_skip & 2) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x ^= pk[j];
-        if (x == 0x12345678u) *reinterpret_cast<uint32_t*>(p.out) = x;   // keeps the math alive
+}
+
+// One warp's slice of a tile (32 rows x BLOCK_N / 4 columns): math per 32-column chunk, the packed rows are
+// written into the warp's staging tile in the TMA swizzle layout of the output box (128-byte rows / SWIZZLE_128B
+// for 64-column slices, 64-byte rows / SWIZZLE_64B for 32-column slices -- conflict-free for a row-per-thread
+// writer) and leave as ONE bulk store per tile; rows beyond the tensor are clipped by the TMA unit.
+template <int EPI, int BLOCK_N>
+__device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, const CUtensorMap* tmap_out, uint32_t stg,
+                                                         uint32_t t_addr, int m_base, int col0, int lane, float rstd, float nmr,
+                                                         uint32_t release_bar) {
+    constexpr int kChunks = BLOCK_N / 128;   // 32-column chunks per slice
+    if (p.dbg_skip & 4) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(release_bar);
         return;
     }
-    // staging tile: 32 rows x 64 B; 16-byte slot s of row r lives at slot s ^ ((r >> 1) & 3)  (conflict-free both ways)
-    const uint32_t srow = stg + lane * 64;
-    const int sw = (lane >> 1) & 3;
-    if (p.tma_store) {
-        // the staging layout IS the TMA SWIZZLE_64B layout of a 32-row x 64-byte box: one bulk store per chunk
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4)
-            sts_v4u(srow + ((s4 ^ sw) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_2d(tmap_out, stg, col0, m_base);
-            tma_store_commit();
+    for (int c = 0; c < kChunks; ++c) {
+        uint32_t pk[16];
+        gemm2_f16_chunk_math<EPI>(p, t_addr + c * 32, col0 + c * 32, lane, rstd, nmr, c + 1 == kChunks ? release_bar : 0u, pk);
+        if (c == 0) {   // the previous tile's store must have read the staging tile (issued a whole main loop ago)
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
         }
-        return;
-    }
+        if constexpr (kChunks == 2) {
+            const uint32_t srow = stg + lane * 128;
 #pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4)
-        sts_v4u(srow + ((s4 ^ sw) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
-    __syncwarp();
-    const int slot = lane & 3;     // this lane's 8-column group
-    const int r0 = lane >> 2;      // rows r0, r0 + 8, r0 + 16, r0 + 24
+            for (int s4 = 0; s4 < 4; ++s4)
+                sts_v4u(srow + (((4 * c + s4) ^ (lane & 7)) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
+        } else {
+            const uint32_t srow = stg + lane * 64;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 8 * i;
-        const int m = m_base + r;
-        const uint4 v = lds_v4u(stg + r * 64 + ((slot ^ ((r >> 1) & 3)) << 4));
-        if (m < p.m_valid && (!(p.dbg_skip & 1) || v.x == 0x12345678u))
-            *reinterpret_cast<uint4*>(static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col0 + slot * 8) = v;
+            for (int s4 = 0; s4 < 4; ++s4)
+                sts_v4u(srow + ((s4 ^ ((lane >> 1) & 3)) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
+        }
     }
+    fence_proxy_async_smem();
     __syncwarp();
+    if (lane == 0 && !(p.dbg_skip & 1)) {
+        tma_store_2d(tmap_out, stg, col0, m_base);
+        tma_store_commit();
+    }
+}
+
+// ---- residual epilogue through TMA (EPI_BIAS_RESID_F32_LN_TMA) ----
+// Same result as EPI_BIAS_RESID_F32_LN, but no byte of the epilogue goes through the LSU (measured at about
+// one 32-byte sector per clock and SM, which made the LSU version of the out_proj epilogue 3x longer than its
+// main loop).  Per warp and 32 x 32 chunk: the residual chunk arrives by TMA in a SWIZZLE_128B tile (loads run
+// kResidBufs - 1 chunks ahead, across tiles), each thread adds its accumulator row IN PLACE (row per thread,
+// 16-byte slots XOR-swizzled by row & 7: conflict-free), accumulates its row's sum / sum of squares in
+// registers (no shuffles), writes the packed fp16 row into a SWIZZLE_64B tile, and two bulk stores write
+// the fp32 chunk back to x and the fp16 chunk to xh.  The fp32 tensor map (tmap_out) serves load and store.
+__device__ __forceinline__ void tma_load_2d_plain(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
 }
 
 // p.m_tiles counts 256-row pair tiles.  Launched with cudaLaunchKernelEx + cluster dimension 2.
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(EpiTraits<EPI>::kThreads, 1)
 gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-    using L = Gemm2Smem<BLOCK_N>;
+                        const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out16,
+                        const GemmParams p) {
+    using L = Gemm2Smem<BLOCK_N, EPI>;
     using T = EpiTraits<EPI>;
     constexpr int kStages = L::kStages;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
@@ -323,6 +361,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     uint64_t* tmem_full = bars + 2 * kStages;       // [2]
     uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* tmem_ptr_bars = bars + 2 * kStages + 5;   // [8 warps][kResidBufs]  (EPI_BIAS_RESID_F32_LN_TMA only)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -334,7 +373,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if (p.tma_store) tma_prefetch_desc(&tmap_out);
+        if constexpr (T::kF16 || T::kTmaResid) tma_prefetch_desc(&tmap_out);
+        if constexpr (T::kTmaResid) tma_prefetch_desc(&tmap_out16);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -343,6 +383,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 2 * T::kWarps);
         }
+        if constexpr (T::kTmaResid)
+            for (int i = 0; i < 8 * kResidBufs; ++i) mbar_init(&tmem_ptr_bars[i], 1);
         fence_barrier_init();
     }
     pdl_launch_dependents();
@@ -383,12 +425,18 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
+#ifdef MCM_GEMM_TRACE
+            long long t_acc = 0, t_full = 0, t_all = clock64(), n_t = 0;
+#define MCM_TR(var, stmt) { const long long t0__ = clock64(); stmt; var += clock64() - t0__; }
+#else
+#define MCM_TR(var, stmt) { stmt; }
+#endif
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                MCM_TR(t_acc, mbar_wait(&tmem_empty[as], aphase ^ 1));
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BLOCK_N;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    MCM_TR(t_full, mbar_wait(&full_bar[stage], phase));
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                     const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
@@ -401,7 +449,18 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 }
                 umma_commit_cta2_mc(&tmem_full[as], 3);
                 if (++as == 2) { as = 0; aphase ^= 1; }
+#ifdef MCM_GEMM_TRACE
+                ++n_t;
+#endif
             }
+#ifdef MCM_GEMM_TRACE
+            if (p.trace) {   // MMA issuer: cycles blocked on a free accumulator / on operand data, total, tiles
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 0), (unsigned long long)t_acc);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 1), (unsigned long long)t_full);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 2), (unsigned long long)(clock64() - t_all));
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 3), (unsigned long long)n_t);
+            }
+#endif
         }
     } else {
         // ===== epilogue warps (both CTAs): TMEM -> registers -> smem transpose -> coalesced HBM =====
@@ -412,8 +471,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         if constexpr (T::kF16) {
             const int slice = ew >> 2;                  // which quarter of the tile's columns this warp drains
             constexpr int kSliceCols = BLOCK_N / 4;
-            constexpr int kChunks = kSliceCols / 32;    // 32-column chunks per warp
-            const uint32_t stg = smem_u32(staging + ew * 2048);
+            const uint32_t stg = smem_u32(staging + ew * (kSliceCols * 64));
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m_blk = tile / p.n_tiles;
                 const int n_blk = tile - m_blk * p.n_tiles;
@@ -440,21 +498,135 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     rstd = rsqrtf(fmaxf(s2 * p.inv_k - mu * mu, 0.f) + p.eps);
                     nmr = -mu * rstd;
                 }
+#ifdef MCM_GEMM_TRACE
+                const long long tw0 = clock64();
+#endif
                 mbar_wait(&tmem_full[as], aphase);
+#ifdef MCM_GEMM_TRACE
+                const long long tw1 = clock64();
+#endif
                 tcgen05_fence_after();
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + slice * kSliceCols;
+                const uint32_t release_bar = mapa_shared(smem_u32(&tmem_empty[as]), 0);   // the pair leader's barrier
                 if (m_base < p.m_valid) {
-#pragma unroll
-                    for (int c = 0; c < kChunks; ++c)
-                        gemm2_epilogue_chunk_f16<EPI>(p, &tmap_out, stg, t_row + c * 32, m_base, col_base + c * 32, lane, rstd, nmr);
+                    gemm2_epilogue_slice_f16<EPI, BLOCK_N>(p, &tmap_out, stg, t_row, m_base, col_base, lane, rstd, nmr, release_bar);
+                } else {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(release_bar);
                 }
-                tcgen05_fence_before();
+#ifdef MCM_GEMM_TRACE
+                if (p.trace && warp == 2 && lane == 0 && rank == 0) {   // one epilogue warp per cluster: wait / busy cycles
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 4), (unsigned long long)(tw1 - tw0));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 5), (unsigned long long)(clock64() - tw1));
+                }
+#endif
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        } else if constexpr (T::kTmaResid) {
+            const int half = ew >> 2;               // which half of the tile's columns this warp drains
+            constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp and tile
+            const uint32_t wbase = smem_u32(staging + ew * kResidWarpBytes);   // [kResidBufs][4 KB] residual / fp32 out, then 2 KB fp16 out
+            const uint32_t hbuf = wbase + kResidBufs * 4096;
+            uint64_t* rbar = tmem_ptr_bars + ew * kResidBufs;                  // this warp's "residual chunk landed" barriers
+            const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+            const int n_chunks = my_tiles * kChunks;
+            // chunk g of this warp -> (global row of the warp's first row, first column)
+            auto chunk_pos = [&](int g, int& m0, int& c0) {
+                const int tile = cluster_id + (g / kChunks) * num_clusters;
+                const int m_blk = tile / p.n_tiles;
+                const int n_blk = tile - m_blk * p.n_tiles;
+                m0 = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
+                c0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + (g % kChunks) * 32;
+            };
+            auto issue_load = [&](int g) {   // lane 0 only
+                int m0, c0;
+                chunk_pos(g, m0, c0);
+                const uint32_t bar = smem_u32(&rbar[g % kResidBufs]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4096) : "memory");
+                tma_load_2d_plain(wbase + (g % kResidBufs) * 4096, &tmap_out, bar, c0, m0);
+            };
+            // (an HBM -> L2 prefetch of the residual one tile ahead was measured slower: the chunk time is set by the
+            // queueing of this warp's bulk copies behind the operand loads in the SM's TMA unit, not by HBM latency)
+            if (lane == 0)
+                for (int g = 0; g < kResidBufs - 1 && g < n_chunks; ++g) issue_load(g);
+            float s1 = 0.f, s2 = 0.f;
+            for (int g = 0; g < n_chunks; ++g) {
+                const int c = g % kChunks;
+                int m_base, col0;
+                chunk_pos(g, m_base, col0);
+                if (c == 0) {
+#ifdef MCM_GEMM_TRACE
+                    const long long tw0 = clock64();
+#endif
+                    mbar_wait(&tmem_full[as], aphase);
+#ifdef MCM_GEMM_TRACE
+                    if (p.trace && warp == 2 && lane == 0 && rank == 0)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 4), (unsigned long long)(clock64() - tw0));
+#endif
+                    tcgen05_fence_after();
+                }
+#ifdef MCM_GEMM_TRACE
+                const long long tb0 = clock64();
+#endif
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2) + c * 32, acc);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform: broadcast loads
+                // every bulk store committed so far has read its smem source: the fp16 tile and the buffer of chunk g - 1
+                // are free; start the load that runs kResidBufs - 1 chunks ahead into the latter
+                if (lane == 0) {
+                    tma_store_wait_read();
+                    if (g + kResidBufs - 1 < n_chunks) issue_load(g + kResidBufs - 1);
+                }
+                tmem_ld_wait();
+                if (c + 1 == kChunks) {   // accumulator stage drained into registers: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+                mbar_wait(&rbar[g % kResidBufs], (g / kResidBufs) & 1);
+                const uint32_t rrow = wbase + (g % kResidBufs) * 4096 + lane * 128;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t a = rrow + ((j ^ (lane & 7)) << 4);
+                    float4 v = lds_v4(a);
+                    const float4 b = __ldg(b4 + j);
+                    v.x += __uint_as_float(acc[4 * j + 0]) + b.x;
+                    v.y += __uint_as_float(acc[4 * j + 1]) + b.y;
+                    v.z += __uint_as_float(acc[4 * j + 2]) + b.z;
+                    v.w += __uint_as_float(acc[4 * j + 3]) + b.w;
+                    sts_v4(a, v);
+                    s1 += (v.x + v.y) + (v.z + v.w);
+                    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                    pk[2 * j + 0] = pack_op16x2(v.x, v.y);
+                    pk[2 * j + 1] = pack_op16x2(v.z, v.w);
+                }
+                __syncwarp();   // lane 0's tma_store_wait_read above covers the fp16 tile for every lane from here on
+                {
+                    const uint32_t hrow = hbuf + lane * 64;
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        sts_v4u(hrow + ((s4 ^ ((lane >> 1) & 3)) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
+                }
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (rank == 0) mbar_arrive(&tmem_empty[as]);
-                    else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                    tma_store_2d(&tmap_out, wbase + (g % kResidBufs) * 4096, col0, m_base);
+                    tma_store_2d(&tmap_out16, hbuf, col0, m_base);
+                    tma_store_commit();
                 }
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (c + 1 == kChunks) {   // this thread's row is complete for this half tile
+                    const int m = m_base + lane;
+                    const int n_blk = (col0 - half * (BLOCK_N / 2)) / BLOCK_N;
+                    if (m < p.m_valid) p.stats_out[static_cast<size_t>(n_blk * 2 + half) * p.stats_ld + m] = make_float2(s1, s2);
+                    s1 = s2 = 0.f;
+                }
+#ifdef MCM_GEMM_TRACE
+                if (p.trace && warp == 2 && lane == 0 && rank == 0)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 5), (unsigned long long)(clock64() - tb0));
+#endif
             }
         } else {
             const int half = ew >> 2;               // which half of the tile's columns this warp drains
@@ -482,7 +654,13 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 float s1[8], s2[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+#ifdef MCM_GEMM_TRACE
+                const long long tw0 = clock64();
+#endif
                 mbar_wait(&tmem_full[as], aphase);
+#ifdef MCM_GEMM_TRACE
+                const long long tw1 = clock64();
+#endif
                 tcgen05_fence_after();
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
 #pragma unroll
@@ -520,6 +698,12 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 }
                 tcgen05_fence_before();
                 __syncwarp();
+#ifdef MCM_GEMM_TRACE
+                if (p.trace && warp == 2 && lane == 0 && rank == 0) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 4), (unsigned long long)(tw1 - tw0));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 5), (unsigned long long)(clock64() - tw1));
+                }
+#endif
                 if (lane == 0) {
                     if (rank == 0) mbar_arrive(&tmem_empty[as]);
                     else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
@@ -529,8 +713,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
     }
 
-    if constexpr (T::kF16) {
-        if (warp >= 2 && lane == 0 && p.tma_store) tma_store_wait_all();   // bulk stores must have completed before the CTA exits
+    if constexpr (T::kF16 || T::kTmaResid) {
+        if (warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores must have completed before the CTA exits
     }
     __syncwarp();
     tcgen05_fence_before();

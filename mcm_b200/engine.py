@@ -189,11 +189,17 @@ class McmEngine:
                                               _ptr(c), _ptr(d), N, K, self._stream()))
         return w16, c, d
 
-    def dbg_gemm_resid_ln(self, a, w, bias, resid):
-        """out = resid + A @ W^T + bias (fp32), its fp16 copy and the partial row statistics [parts, M, 2]."""
+    def dbg_gemm_resid_ln(self, a, w, bias, resid, in_place: bool = False, mutate: bool = False):
+        """out = resid + A @ W^T + bias (fp32), its fp16 copy and the partial row statistics [parts, M, 2].
+        ``in_place`` aliases resid and out like the forward does (K <= 1024 then takes the TMA epilogue)."""
         M, K = a.shape
         N = w.shape[0]
-        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        if mutate:
+            out = resid          # timing runs: update the caller's tensor itself
+        else:
+            out = resid.clone().contiguous() if in_place else torch.empty((M, N), dtype=torch.float32, device=self.device)
+        if in_place:
+            resid = out
         out16 = torch.empty((M, N), dtype=torch.float16, device=self.device)
         stats = torch.zeros((N // 64, M, 2), dtype=torch.float32, device=self.device)
         parts = C.c_int32(0)

@@ -77,9 +77,9 @@ LN_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("gelu,in_place", [(False, False), (True, False), (False, True)])
 @pytest.mark.parametrize("M,D,K1,N2", LN_SHAPES)
-def test_gemm_layernorm_fold_matches_torch(engine_factory, M, D, K1, N2, gelu):
+def test_gemm_layernorm_fold_matches_torch(engine_factory, M, D, K1, N2, gelu, in_place):
     eng, _, _ = engine_factory("tiny", 5, 8)
     g = torch.Generator(device="cuda").manual_seed(M + D + K1 + N2)
     a = torch.randn(M, K1, device="cuda", generator=g).to(torch.float16)
@@ -93,7 +93,8 @@ def test_gemm_layernorm_fold_matches_torch(engine_factory, M, D, K1, N2, gelu):
     w_p = torch.randn(N2, D, device="cuda", generator=g) * D ** -0.5
     b_p = torch.randn(N2, device="cuda", generator=g)
 
-    x, x16, stats = eng.dbg_gemm_resid_ln(a, w_o, b_o, resid)
+    # in_place aliases the residual and the output like the forward does: the epilogue then runs through TMA
+    x, x16, stats = eng.dbg_gemm_resid_ln(a, w_o, b_o, resid, in_place=in_place)
     w16, c, d = eng.dbg_fold_ln(w_p, gamma, beta, b_p)
     y = eng.dbg_gemm_ln(x16, w16, d, c, stats, D, gelu=gelu)
     torch.cuda.synchronize()

@@ -37,7 +37,7 @@ for N, K, epi in CASES:
         cvec = torch.randn(N, device="cuda", generator=g)
         run = lambda: eng.dbg_gemm_ln(a, w, bias, cvec, stats, K, gelu=(epi == 5))
     elif epi == 6:
-        run = lambda: eng.dbg_gemm_resid_ln(a, w, bias, resid)
+        run = lambda: eng.dbg_gemm_resid_ln(a, w, bias, resid, in_place=True, mutate=True)
     else:
         run = lambda: eng.dbg_gemm(a, w, bias, resid, epi)
     for _ in range(3):
