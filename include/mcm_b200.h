@@ -113,6 +113,20 @@ int mcm_score(McmHandle* h, const float* images_dev, int32_t b, float T, int32_t
 int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int32_t batch, float T,
                           int32_t score_kind, float* scores_host);
 
+/* uint8 ingest.  Same three calls, but the images are what the reference's preprocess holds
+ * BEFORE its last two steps (utils/train_eval_util.py:29-34: Resize(224) -> CenterCrop(224) -> ToTensor -> Normalize):
+ * uint8 [b, image_size, image_size, 3] HWC, the layout of a decoded PIL image / JPEG decoder output.  ToTensor
+ * (x / 255) and Normalize ((x - mean) / std, fp32, torchvision's operation order) are fused into the patch gather,
+ * so the fp16 patch rows -- and therefore features and scores -- are bit-identical to mcm_score on the fp32 tensor
+ * the reference's DataLoader would have produced, at a quarter of the PCIe and HBM bytes.
+ * mcm_set_normalization replaces the default CLIP constants (utils/train_eval_util.py:27-28). */
+int mcm_set_normalization(McmHandle* h, const float* mean3, const float* std3);
+int mcm_image_features_u8(McmHandle* h, const uint8_t* images_dev, int32_t b, float* feats_dev, void* stream);
+int mcm_score_u8(McmHandle* h, const uint8_t* images_dev, int32_t b, float T, int32_t score_kind, float* scores_dev,
+                 void* stream);
+int mcm_score_stream_host_u8(McmHandle* h, const uint8_t* images_host, int64_t n, int32_t batch, float T,
+                             int32_t score_kind, float* scores_host);
+
 /* Number of kernels of this library launched on the handle's device since the last reset
  * (bench.py reports it as `gpu_launches`). */
 int64_t mcm_launch_count(const McmHandle* h);

@@ -44,6 +44,10 @@ SIGNATURES = {
     "mcm_image_features": (C.c_int, [_H, _P, C.c_int32, _P, _P]),
     "mcm_score": (C.c_int, [_H, _P, C.c_int32, C.c_float, C.c_int32, _P, _P]),
     "mcm_score_stream_host": (C.c_int, [_H, _P, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
+    "mcm_set_normalization": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "mcm_image_features_u8": (C.c_int, [_H, _P, C.c_int32, _P, _P]),
+    "mcm_score_u8": (C.c_int, [_H, _P, C.c_int32, C.c_float, C.c_int32, _P, _P]),
+    "mcm_score_stream_host_u8": (C.c_int, [_H, _P, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
     "mcm_launch_count": (C.c_int64, [_H]),
     "mcm_reset_launch_count": (None, [_H]),
     "mcm_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),

@@ -102,7 +102,10 @@ struct McmHandle {
     bool attn_split = false;           // env MCM_ATTN_SPLIT=1: two threads per query row (16 softmax warps), keys_pad <= 208
     bool cls_shortcut = true;
 
-    // host-stream path
+    // uint8 ingest: Normalize constants of the reference preprocess (utils/train_eval_util.py:27-28)
+    NormConst norm{{0.48145466f, 0.4578275f, 0.40821073f}, {0.26862954f, 0.26130258f, 0.27577711f}};
+
+    // host-stream path (img_buf holds fp32 NCHW or uint8 NHWC batches: sized for the larger)
     float* img_buf[2] = {nullptr, nullptr};
     float* scores_buf = nullptr;
     int64_t scores_cap = 0;
@@ -509,10 +512,16 @@ int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T,
     return MCM_OK;
 }
 
-int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
+// images: fp32 NCHW already normalised (u8 == false) or uint8 NHWC straight from the decoder (u8 == true)
+int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st) {
     {
         ProfScope prof(h, MCM_PROF_PATCHIFY, st);
-        MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), 0, st, 1, images, h->patches, h->G, h->cfg.patch, h->Kp));
+        if (u8)
+            MCM_CUDA(h, launch_k(patchify_u8_kernel, dim3(b * h->G), dim3(256), 0, st, 1, static_cast<const uint8_t*>(images), h->patches,
+                                 h->G, h->cfg.patch, h->Kp, h->norm));
+        else
+            MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), 0, st, 1, static_cast<const float*>(images), h->patches,
+                                 h->G, h->cfg.patch, h->Kp));
     }
     h->launches++;
     int rc = launch_gemm(h, MCM_PROF_GEMM_PATCH, h->tm_patches, h->tm_wpatch, b * h->Np, h->D, h->Kp, EPI_POS_F32, nullptr, h->x, nullptr,
@@ -534,8 +543,8 @@ int launch_embed(McmHandle* h, const float* images, int b, cudaStream_t st) {
 
 // embeddings + encoder.  Returns in *pooled / *pooled_stride where the rows the tail pools live:
 // the CLS rows of h->x (stride S * D) or, with the last-layer shortcut, the compact h->x_cls (stride D).
-int forward_tower(McmHandle* h, const float* images, int b, cudaStream_t st, const float** pooled, size_t* pooled_stride) {
-    int rc = launch_embed(h, images, b, st);
+int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st, const float** pooled, size_t* pooled_stride) {
+    int rc = launch_embed(h, images, u8, b, st);
     if (rc) return rc;
     const int M = b * h->S, D = h->D, F = h->F;
     *pooled = h->x;
@@ -915,7 +924,11 @@ int mcm_set_text_bank(McmHandle* h, const float* bank, int32_t K, int32_t alread
     return MCM_OK;
 }
 
-int mcm_image_features(McmHandle* h, const float* images, int32_t b, float* feats, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int image_features_any(McmHandle* h, const void* images, bool u8, int32_t b, float* feats, void* stream) {
     int rc = check_ready(h, b, false);
     if (rc) return rc;
     if (b == 0) return MCM_OK;
@@ -923,11 +936,11 @@ int mcm_image_features(McmHandle* h, const float* images, int32_t b, float* feat
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float* pooled = nullptr;
     size_t stride = 0;
-    if ((rc = forward_tower(h, images, b, st, &pooled, &stride))) return rc;
+    if ((rc = forward_tower(h, images, u8, b, st, &pooled, &stride))) return rc;
     return launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, feats, nullptr, st);
 }
 
-int mcm_score(McmHandle* h, const float* images, int32_t b, float T, int32_t kind, float* scores, void* stream) {
+int score_any(McmHandle* h, const void* images, bool u8, int32_t b, float T, int32_t kind, float* scores, void* stream) {
     int rc = check_ready(h, b, true);
     if (rc) return rc;
     if (b == 0) return MCM_OK;
@@ -937,19 +950,63 @@ int mcm_score(McmHandle* h, const float* images, int32_t b, float T, int32_t kin
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float* pooled = nullptr;
     size_t stride = 0;
-    if ((rc = forward_tower(h, images, b, st, &pooled, &stride))) return rc;
+    if ((rc = forward_tower(h, images, u8, b, st, &pooled, &stride))) return rc;
     return launch_tail(h, pooled, stride, b, T, kind, nullptr, scores, st);
 }
 
+int score_stream_host_any(McmHandle* h, const void* images_host_v, bool u8, int64_t n, int32_t batch, float T, int32_t kind,
+                          float* scores_host);
+
+}  // namespace
+
+extern "C" {
+
+int mcm_image_features(McmHandle* h, const float* images, int32_t b, float* feats, void* stream) {
+    return image_features_any(h, images, false, b, feats, stream);
+}
+int mcm_image_features_u8(McmHandle* h, const uint8_t* images, int32_t b, float* feats, void* stream) {
+    return image_features_any(h, images, true, b, feats, stream);
+}
+int mcm_score(McmHandle* h, const float* images, int32_t b, float T, int32_t kind, float* scores, void* stream) {
+    return score_any(h, images, false, b, T, kind, scores, stream);
+}
+int mcm_score_u8(McmHandle* h, const uint8_t* images, int32_t b, float T, int32_t kind, float* scores, void* stream) {
+    return score_any(h, images, true, b, T, kind, scores, stream);
+}
 int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int32_t batch, float T, int32_t kind,
+                          float* scores_host) {
+    return score_stream_host_any(h, images_host, false, n, batch, T, kind, scores_host);
+}
+int mcm_score_stream_host_u8(McmHandle* h, const uint8_t* images_host, int64_t n, int32_t batch, float T, int32_t kind,
+                             float* scores_host) {
+    return score_stream_host_any(h, images_host, true, n, batch, T, kind, scores_host);
+}
+
+int mcm_set_normalization(McmHandle* h, const float* mean3, const float* std3) {
+    if (!h || !mean3 || !std3) return fail(h, MCM_EINVAL, "mcm_set_normalization: NULL argument");
+    for (int c = 0; c < 3; ++c) {
+        if (!(std3[c] > 0.f)) return fail(h, MCM_EINVAL, "std[%d] must be positive (got %g)", c, (double)std3[c]);
+        h->norm.mean[c] = mean3[c];
+        h->norm.std[c] = std3[c];
+    }
+    return MCM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int score_stream_host_any(McmHandle* h, const void* images_host_v, bool u8, int64_t n, int32_t batch, float T, int32_t kind,
                           float* scores_host) {
     int rc = check_ready(h, batch, true);
     if (rc) return rc;
     if (n == 0) return MCM_OK;
     if (n < 0 || batch <= 0) return fail(h, MCM_EINVAL, "n must be >= 0 and batch positive");
-    if (!images_host || !scores_host) return fail(h, MCM_EINVAL, "mcm_score_stream_host: NULL buffer");
+    if (!images_host_v || !scores_host) return fail(h, MCM_EINVAL, "mcm_score_stream_host: NULL buffer");
     MCM_CUDA(h, cudaSetDevice(h->cfg.device));
     const size_t img_elems = (size_t)3 * h->cfg.image_size * h->cfg.image_size;
+    const size_t esz = u8 ? 1 : sizeof(float);
+    const uint8_t* images_host = static_cast<const uint8_t*>(images_host_v);
     if (!h->s_copy) {
         MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
         MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
@@ -972,11 +1029,11 @@ int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int
         const int cur = static_cast<int>(std::min<int64_t>(batch, n - done));
         const int slot = it & 1;
         if (it >= 2) MCM_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_done[slot], 0));
-        MCM_CUDA(h, cudaMemcpyAsync(h->img_buf[slot], images_host + (size_t)done * img_elems, (size_t)cur * img_elems * sizeof(float),
+        MCM_CUDA(h, cudaMemcpyAsync(h->img_buf[slot], images_host + (size_t)done * img_elems * esz, (size_t)cur * img_elems * esz,
                                     cudaMemcpyHostToDevice, h->s_copy));
         MCM_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_copy));
         MCM_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
-        if ((rc = mcm_score(h, h->img_buf[slot], cur, T, kind, h->scores_buf + done, h->s_comp))) return rc;
+        if ((rc = score_any(h, h->img_buf[slot], u8, cur, T, kind, h->scores_buf + done, h->s_comp))) return rc;
         MCM_CUDA(h, cudaEventRecord(h->ev_done[slot], h->s_comp));
         done += cur;
         ++it;
@@ -985,6 +1042,10 @@ int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int
     MCM_CUDA(h, cudaStreamSynchronize(h->s_comp));
     return MCM_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int64_t mcm_launch_count(const McmHandle* h) { return h ? h->launches : 0; }
 void mcm_reset_launch_count(McmHandle* h) { if (h) h->launches = 0; }
@@ -1120,7 +1181,7 @@ int mcm_dbg_embed(McmHandle* h, const float* images, int32_t b, float* x, void* 
     if (!images || !x) return fail(h, MCM_EINVAL, "mcm_dbg_embed: NULL argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // run only pre_layrnorm here: the fused LN1 output goes to the workspace, x is copied out
-    if ((rc = launch_embed(h, images, b, st))) return rc;
+    if ((rc = launch_embed(h, images, false, b, st))) return rc;
     MCM_CUDA(h, cudaMemcpyAsync(x, h->x, (size_t)b * h->S * h->D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return MCM_OK;
 }

@@ -194,6 +194,51 @@ patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int
     }
 }
 
+// uint8 ingest: the last two steps of the reference preprocess fused into the patch gather.
+//   images u8 [b, H, W, 3] HWC (what PIL / a JPEG decoder holds after Resize(224) + CenterCrop(224),
+//   utils/train_eval_util.py:29-34)  ->  ToTensor (x / 255)  ->  Normalize ((x - mean[c]) / std[c], :27-28)
+//   ->  patches fp16 [b * G * G, Kp],  column = c * p * p + i * p + j
+// fp32 arithmetic in torchvision's order (true divisions), so the fp16 patch rows are bit-identical to
+// patchify_kernel run on the fp32 tensor the reference's DataLoader would have produced -- at a quarter of the
+// PCIe / HBM bytes.  One CTA handles the p image rows of one row of G patches: reads are contiguous 3 W-byte
+// pixel rows (16-byte vector loads when W * 3 is a multiple of 16), writes are fp16 pairs.
+struct NormConst { float mean[3], std[3]; };
+
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp, const NormConst nc) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int W = G * p;
+    const int gy = blockIdx.x % G;
+    const int b = blockIdx.x / G;
+    const int row_bytes = 3 * W;                  // one pixel row, HWC
+    const uint8_t* src = img + (static_cast<size_t>(b) * W + static_cast<size_t>(gy) * p) * row_bytes;
+    op16_t* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
+    // item = 2 horizontally adjacent pixels (6 bytes) of image row i: x is even and p is even, so both land in one patch
+    const int half_w = W >> 1;
+    const int n = p * half_w;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int xh = t % half_w;
+        const int i = t / half_w;
+        const int x = xh * 2;
+        const uint8_t* q = src + static_cast<size_t>(i) * row_bytes + 3 * x;   // 6-byte run, 2-byte aligned
+        const uint16_t w0 = __ldg(reinterpret_cast<const uint16_t*>(q));
+        const uint16_t w1 = __ldg(reinterpret_cast<const uint16_t*>(q + 2));
+        const uint16_t w2 = __ldg(reinterpret_cast<const uint16_t*>(q + 4));
+        const float px0[3] = {static_cast<float>(w0 & 0xff), static_cast<float>(w0 >> 8), static_cast<float>(w1 & 0xff)};
+        const float px1[3] = {static_cast<float>(w1 >> 8), static_cast<float>(w2 & 0xff), static_cast<float>(w2 >> 8)};
+        const int gx = x / p;
+        const int j = x - gx * p;
+        op16_t* d = dst_row + static_cast<size_t>(gx) * Kp + i * p + j;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float a = __fdiv_rn(__fsub_rn(__fdiv_rn(px0[c], 255.0f), nc.mean[c]), nc.std[c]);
+            const float e = __fdiv_rn(__fsub_rn(__fdiv_rn(px1[c], 255.0f), nc.mean[c]), nc.std[c]);
+            *reinterpret_cast<uint32_t*>(d + c * p * p) = pack_op16x2(a, e);
+        }
+    }
+}
+
 // fp32 -> fp16 with row re-striding (weight packing): dst[r * dst_ld + c] = src[r * cols + c]
 __global__ void convert_rows_f16_kernel(const float* __restrict__ src, op16_t* __restrict__ dst, int64_t rows,
                                          int cols, int dst_ld) {

@@ -126,6 +126,26 @@ class McmEngine:
             raise ValueError(f"batch {images.shape[0]} exceeds max_batch {self.max_batch}")
         return int(images.shape[0])
 
+    def _check_images_u8(self, images: torch.Tensor, device) -> int:
+        c = self.cfg
+        if not torch.is_tensor(images) or images.dim() != 4 or images.shape[3] != 3:
+            raise ValueError("uint8 images must be a [b, H, W, 3] tensor (HWC, as decoded)")
+        if images.shape[1] != c.image_size or images.shape[2] != c.image_size:
+            raise ValueError(f"Input image size ({images.shape[1]}*{images.shape[2]}) doesn't match model "
+                             f"({c.image_size}*{c.image_size}).")
+        if images.dtype != torch.uint8:
+            raise ValueError(f"uint8 ingest needs a torch.uint8 tensor, got {images.dtype}")
+        if device is not None and images.device != device:
+            raise ValueError(f"images must live on {device}, got {images.device}")
+        return int(images.shape[0])
+
+    def set_normalization(self, mean, std) -> None:
+        """Constants of the fused ``ToTensor -> Normalize`` of the uint8 ingest (default: the CLIP constants of
+        ``utils/train_eval_util.py:27-28``)."""
+        m = (C.c_float * 3)(*[float(v) for v in mean])
+        s = (C.c_float * 3)(*[float(v) for v in std])
+        self._check(self._lib.mcm_set_normalization(self._h, m, s))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -149,6 +169,44 @@ class McmEngine:
             raise ValueError("out must be a contiguous float32 device tensor with at least b elements")
         self._check(self._lib.mcm_score(self._h, _ptr(x), b, float(T), _score_kind(score), _ptr(out), self._stream()))
         return out[:b]
+
+    def image_features_u8(self, images_u8: torch.Tensor) -> torch.Tensor:
+        """``get_image_features`` from decoded uint8 ``[b, H, W, 3]`` pixels (ToTensor + Normalize fused on the device)."""
+        b = self._check_images_u8(images_u8, self.device)
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        out = torch.empty((b, self.cfg.proj), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_image_features_u8(self._h, _ptr(images_u8.contiguous()), b, _ptr(out), self._stream()))
+        return out
+
+    def score_u8(self, images_u8: torch.Tensor, T: float = 1.0, score: str = "MCM",
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """:meth:`score` from decoded uint8 ``[b, H, W, 3]`` device pixels."""
+        b = self._check_images_u8(images_u8, self.device)
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        if out is None:
+            out = torch.empty((b,), dtype=torch.float32, device=self.device)
+        elif out.numel() < b or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 device tensor with at least b elements")
+        self._check(self._lib.mcm_score_u8(self._h, _ptr(images_u8.contiguous()), b, float(T), _score_kind(score), _ptr(out),
+                                           self._stream()))
+        return out[:b]
+
+    def score_stream_host_u8(self, images_host_u8, batch: Optional[int] = None, T: float = 1.0,
+                             score: str = "MCM") -> np.ndarray:
+        """:meth:`score_stream_host` from uint8 ``[n, H, W, 3]`` HOST pixels: 4x fewer PCIe bytes."""
+        t = torch.as_tensor(images_host_u8)
+        if t.device.type != "cpu":
+            raise ValueError("images_host_u8 must be a CPU tensor / ndarray")
+        n = self._check_images_u8(t, None)
+        t = t.contiguous()
+        batch = int(batch or self.max_batch)
+        out = np.empty((n,), dtype=np.float32)
+        if n:
+            self._check(self._lib.mcm_score_stream_host_u8(self._h, _ptr(t), n, batch, float(T), _score_kind(score),
+                                                           C.c_void_p(out.ctypes.data)))
+        return out
 
     def score_stream_host(self, images_host, batch: Optional[int] = None, T: float = 1.0,
                           score: str = "MCM") -> np.ndarray:

@@ -110,6 +110,11 @@ def synth_images(n: int, seed: int, image_size: int = 224, mean: float = 0.0, st
     return x
 
 
+def synth_images_u8(n: int, seed: int, image_size: int = 224) -> np.ndarray:
+    """``[n, H, W, 3]`` uint8 "decoded" pixels (HWC, uniform over 0..255) for the uint8 ingest path."""
+    return _rng(seed, 7).integers(0, 256, size=(n, image_size, image_size, 3), dtype=np.uint8)
+
+
 def synth_prototype_stream(n: int, protos: np.ndarray, seed: int, noise: float) -> np.ndarray:
     """ID stream of the prototype harness: image i = prototype[i % K] + noise * N(0,1)."""
     K = protos.shape[0]

@@ -68,6 +68,25 @@ CFGS = {
 }
 
 
+# the Normalize constants of the reference preprocess, utils/train_eval_util.py:27-28
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def preprocess_u8(images_u8, mean=CLIP_MEAN, std=CLIP_STD):
+    """Last two steps of the reference ``val_preprocess`` (``utils/train_eval_util.py:29-34``) on decoded pixels:
+    ``ToTensor`` (torchvision ``functional.to_tensor``: HWC uint8 -> CHW, ``.to(float32).div(255)``) then
+    ``Normalize`` (``functional.normalize``: ``tensor.sub_(mean).div_(std)`` with fp32 ``mean`` / ``std`` tensors).
+    ``images_u8``: uint8 ``[n, H, W, 3]`` -> fp32 ``[n, 3, H, W]``.  Pinned against torchvision itself on PIL images
+    in ``tests/test_oracle_golden.py``."""
+    x = torch.as_tensor(images_u8)
+    assert x.dtype == torch.uint8 and x.dim() == 4 and x.shape[3] == 3
+    x = x.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    sd = torch.as_tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    return x.sub_(m).div_(sd)
+
+
 def _ln(x, w, b, eps):
     """nn.LayerNorm: biased variance, eps inside the sqrt, affine (HF:359-361,659-661)."""
     mu = x.mean(dim=-1, keepdim=True)

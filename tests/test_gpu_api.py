@@ -152,3 +152,44 @@ def test_cls_shortcut_is_equivalent(engine_factory, cfg_name):
     rel = ((a_f - b_f).norm(dim=1) / b_f.norm(dim=1)).max().item()
     assert rel <= 2e-3, rel
     assert (a_s - b_s).abs().max().item() <= 2e-5
+
+
+def test_uint8_ingest_is_bit_identical_to_fp32_path(tiny_net):
+    """uint8 HWC pixels through the fused ToTensor + Normalize patch gather == the fp32 tensor the reference
+    preprocess (utils/train_eval_util.py:27-34) would have produced, through the fp32 entry points."""
+    from mcm_b200 import synth
+    from oracle import clip_mcm_oracle as O
+    net, cfg, bank = tiny_net
+    eng = net.engine
+    u8 = synth.synth_images_u8(45, 21)
+    f32 = O.preprocess_u8(u8)
+    ref_scores = torch.cat([eng.score(f32[s:s + 32].cuda()) for s in range(0, 45, 32)]).cpu().numpy()
+    ref_feats = eng.image_features(f32[:32].cuda()).cpu()
+    d_u8 = torch.from_numpy(u8).cuda()
+    got = torch.cat([eng.score_u8(d_u8[s:s + 32]) for s in range(0, 45, 32)]).cpu().numpy()
+    np.testing.assert_array_equal(got, ref_scores)
+    assert torch.equal(eng.image_features_u8(d_u8[:32]).cpu(), ref_feats)
+    for batch in (32, 7):
+        np.testing.assert_array_equal(eng.score_stream_host_u8(torch.from_numpy(u8).pin_memory(), batch=batch), ref_scores)
+    np.testing.assert_array_equal(eng.score_stream_host_u8(u8, batch=16), ref_scores)
+    # against the oracle end to end
+    ora = O.ood_scores(f32, eng_sd(tiny_net), cfg, bank, T=1, score="MCM", batch=45)
+    np.testing.assert_allclose(got, ora, rtol=0, atol=1e-3)
+    # other normalisation constants
+    eng.set_normalization((0.5, 0.5, 0.5), (0.25, 0.5, 1.0))
+    try:
+        f2 = O.preprocess_u8(u8[:8], (0.5, 0.5, 0.5), (0.25, 0.5, 1.0))
+        np.testing.assert_array_equal(eng.score_u8(d_u8[:8]).cpu().numpy(), eng.score(f2.cuda()).cpu().numpy())
+    finally:
+        eng.set_normalization(O.CLIP_MEAN, O.CLIP_STD)
+    with pytest.raises(ValueError):
+        eng.score_u8(d_u8[:4, :100])
+    with pytest.raises(ValueError):
+        eng.score_u8(d_u8[:4].float())
+    with pytest.raises(ValueError):
+        eng.set_normalization((0, 0, 0), (1, 0, 1))
+
+
+def eng_sd(tiny_net_fixture):
+    from mcm_b200 import synth
+    return synth.synth_vision_state_dict(tiny_net_fixture[1], 5)

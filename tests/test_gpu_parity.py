@@ -152,3 +152,22 @@ def test_fullsize_stream_metrics(noise, fpr_tol):
         assert abs(m_got[2] - m_ref[2]) <= fpr_tol, (m_got, m_ref)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("cfg_name", ["small", "ViT-L/14"])
+def test_uint8_ingest_patch_geometries(engine_factory, cfg_name):
+    """uint8 ingest on patch 16 and patch 14 (K padding 588 -> 640) towers: bit-identical to the fp32 entry point on
+    the tensor the reference preprocess would have produced, and within tolerance of the oracle."""
+    from mcm_b200 import synth
+    from oracle import clip_mcm_oracle as O
+    eng, sd, cfg = engine_factory(cfg_name, 5, 16)
+    u8 = synth.synth_images_u8(3, 33)
+    f32 = O.preprocess_u8(u8)
+    got = eng.image_features_u8(torch.from_numpy(u8).cuda()).cpu()
+    same = eng.image_features(f32.cuda()).cpu()
+    assert torch.equal(got, same)
+    with torch.no_grad():
+        ref = O.image_features(f32, sd, cfg)
+    rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    report("features_u8", dict(cfg=cfg_name, rel_err=rel))
+    assert rel <= 3e-2, rel

@@ -40,3 +40,17 @@ def test_oracle_b16_subset(golden_dir):
 def test_flops_formula():
     assert O.flops_per_image(O.CFGS["ViT-B/16"], 1000) == pytest.approx(35.128e9, rel=2e-4)
     assert O.flops_per_image(O.CFGS["ViT-L/14"], 1000) == pytest.approx(162.027e9, rel=2e-4)
+
+
+def test_oracle_preprocess_matches_torchvision():
+    """oracle.preprocess_u8 == the ToTensor -> Normalize tail of the reference val_preprocess
+    (utils/train_eval_util.py:27-34) executed by torchvision itself on PIL images, bit for bit."""
+    PIL = pytest.importorskip("PIL.Image")
+    T = pytest.importorskip("torchvision.transforms")
+    from mcm_b200 import synth
+    u8 = synth.synth_images_u8(3, 11)
+    tail = T.Compose([T.ToTensor(), T.Normalize(mean=O.CLIP_MEAN, std=O.CLIP_STD)])
+    ref = torch.stack([tail(PIL.fromarray(u8[i])) for i in range(u8.shape[0])])
+    got = O.preprocess_u8(u8)
+    assert got.dtype == torch.float32 and got.shape == (3, 3, 224, 224)
+    assert torch.equal(got, ref)
