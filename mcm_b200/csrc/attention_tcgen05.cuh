@@ -1,6 +1,12 @@
 // Multi-head self-attention core on the 5th-gen tensor cores:  softmax(Q K^T / 8) V  per (image, head)
-// for sequences of up to 256 tokens (ViT-B/16: 197, ViT-B/32: 50), head dim 64, no mask, not causal
-// (HF:modeling_clip.py:261-279 eager == what SDPA computes, :318-331).
+// for sequences of up to 257 tokens (ViT-B/16: 197, ViT-B/32: 50, ViT-L/14: 257), head dim 64, no mask, not
+// causal (HF:modeling_clip.py:261-279 eager == what SDPA computes, :318-331).
+//
+// 257 = 256 + 1: a UMMA tile is at most 256 keys wide and two fp32 score buffers of more than 256 columns do
+// not fit the 512 columns of tensor memory, so the ONE key beyond 256 of ViT-L/14 ("extra key") never enters
+// the tensor core: every softmax thread computes its row's score against it with 64 FMAs (q row and the key
+// straight from the QKV buffer in L2), folds it into the row max / row sum, and adds p_extra * v_extra to the
+// O row while draining it.  The 256 other keys take the normal path with keys_pad = 256.
 //
 // Persistent CTAs (one per SM) walk over (image, head) items; every item is cut into 128-query-row
 // units.  Warp roles:
@@ -45,7 +51,9 @@ constexpr int kAtcQBytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kAtcStagingBytes = 8 * 32 * 128; // 8 softmax warps x 32 rows x 64 fp16
 
 struct AtcParams {
-    int b, S, H, keys_pad;   // keys_pad: S rounded up to 16 (<= 256)
+    int b, S, H, keys_pad;   // keys_pad: min(S, 256) rounded up to 16
+    int n_extra;             // S - 256 if S > 256 (0 or 1): keys handled outside the tensor core
+    const op16_t* qkv;       // the fused QKV buffer the tensor maps cover (read directly for the extra key)
     int units_per_item;      // ceil(S / 128)
     float scale_log2e;       // dh^-0.5 * log2(e)
     op16_t* out;
@@ -61,6 +69,10 @@ struct AtcParams {
 #else
 #define ATC_TRACE(role, unit, ev) do {} while (0)
 #endif
+
+constexpr int kAtcMaxS = 257;   // 256 tensor-core keys + 1 extra key
+// keys the tensor core sees, rounded up to the UMMA N granularity
+__host__ __device__ inline int atc_keys_pad(int S) { return ((S < 256 ? S : 256) + 15) / 16 * 16; }
 
 __host__ __device__ inline int atc_smem_bytes(int keys_pad) {
     return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
@@ -96,6 +108,25 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "}\n"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// dot product of two 64-element fp16 rows (128 B each, 16-byte aligned), fp32 accumulation
+__device__ __forceinline__ float atc_dot64(const op16_t* __restrict__ a, const op16_t* __restrict__ b) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(a);
+    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 x = __ldg(a4 + j), y = __ldg(b4 + j);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 u = unpack_op16x2(xs[e]), v = unpack_op16x2(ys[e]);
+            acc0 = fmaf(u.x, v.x, acc0);
+            acc1 = fmaf(u.y, v.y, acc1);
+        }
+    }
+    return acc0 + acc1;
 }
 
 // running max over one 32-key chunk of a score row (keys k0 .. k0 + 31; keys >= S are padding)
@@ -264,6 +295,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const int nfull = p.keys_pad >> 5;
         const bool rem16 = (p.keys_pad & 16) != 0;
         const float c = p.scale_log2e;
+        const int S_tc = p.S - p.n_extra;    // keys that go through the tensor core
         // Stagger the two groups by half a period: group 1 starts its first softmax only when group 0 has
         // finished its first one, so from then on one group is in the MUFU-bound softmax while the tensor
         // core serves the other group's P.V / next QK^T (the MMA warp issues in exactly that order).
@@ -278,6 +310,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const int img = item / p.H, h = item - img * p.H;
             const int wrow0 = mt * 128 + quad * 32;       // first query row (within the image) of this warp
             const bool warp_valid = wrow0 < p.S;
+            // the extra key (ViT-L/14's 257th token): this row's raw score against it, on the CUDA cores,
+            // while the tensor core is still busy with Q K^T of the other 256
+            float s_x = 0.f;
+            const op16_t* kv_x = nullptr;
+            if (p.n_extra > 0 && warp_valid) {
+                const size_t ld = static_cast<size_t>(3) * D;
+                kv_x = p.qkv + (static_cast<size_t>(img) * p.S + S_tc) * ld + D + h * 64;     // k of the extra token; v at + D
+                const int row = wrow0 + lane;
+                if (row < p.S) s_x = atc_dot64(p.qkv + (static_cast<size_t>(img) * p.S + row) * ld + h * 64, kv_x);
+            }
             mbar_wait(&s_full[g], j & 1);
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 0);       // S ready
             tcgen05_fence_after();
@@ -292,8 +334,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     tmem_ld_32x32b_x32(t_s + ch * 32, va);
                     if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
                     tmem_ld_wait();
-                    mx = atc_chunk_max(va, ch * 32, p.S, mx);
-                    if (two) mx = atc_chunk_max(vb, ch * 32 + 32, p.S, mx);
+                    mx = atc_chunk_max(va, ch * 32, S_tc, mx);
+                    if (two) mx = atc_chunk_max(vb, ch * 32 + 32, S_tc, mx);
                 }
                 if (rem16) {
                     uint32_t v[16];
@@ -301,8 +343,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (nfull * 32 + e < p.S) mx = fmaxf(mx, __uint_as_float(v[e]));
+                        if (nfull * 32 + e < S_tc) mx = fmaxf(mx, __uint_as_float(v[e]));
                 }
+                if (p.n_extra > 0) mx = fmaxf(mx, s_x);
                 const float mc = mx * c;
                 if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 1);   // pass 1 done
                 // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns.
@@ -316,11 +359,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         tmem_ld_wait();
                         const bool two = ch + 1 < nfull;
                         if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
-                        atc_chunk_exp(va, ch * 32, p.S, c, mc, sum0, sum1, t_s + ch * 16);
+                        atc_chunk_exp(va, ch * 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16);
                         if (two) {
                             tmem_ld_wait();
                             if (ch + 2 < nfull) tmem_ld_32x32b_x32(t_s + ch * 32 + 64, va);
-                            atc_chunk_exp(vb, ch * 32 + 32, p.S, c, mc, sum0, sum1, t_s + ch * 16 + 16);
+                            atc_chunk_exp(vb, ch * 32 + 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16 + 16);
                         }
                     }
                 }
@@ -329,7 +372,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_s + ch * 32, v);
                     tmem_ld_wait();
-                    atc_chunk_exp(v, ch * 32, p.S, c, mc, sum0, sum1, t_s + ch * 16);
+                    atc_chunk_exp(v, ch * 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16);
                 }
 #endif
                 if (rem16) {
@@ -340,8 +383,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int k0 = nfull * 32 + 2 * e;
-                        const float p0 = (k0 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
-                        const float p1 = (k0 + 1 < p.S) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
+                        const float p0 = (k0 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
+                        const float p1 = (k0 + 1 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
                         sum0 += p0;
                         sum1 += p1;
                         pk[e] = pack_op16x2(p0, p1);
@@ -350,6 +393,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 }
                 tmem_st_wait();
                 row_sum = sum0 + sum1;
+                if (p.n_extra > 0) {   // s_x becomes the probability of the extra key, rounded like the P operand
+                    const float px = ex2_approx(fmaf(s_x, c, -mc));
+                    row_sum += px;
+                    s_x = unpack_op16x2(pack_op16x2(px, 0.f)).x;
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -367,6 +415,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_s + 128 + hc * 32, v);
                     tmem_ld_wait();
+                    if (p.n_extra > 0) {   // O += p_extra * v_extra (warp-uniform addresses: broadcast loads)
+                        const uint4* vx = reinterpret_cast<const uint4*>(kv_x + D + hc * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 w = __ldg(vx + q);
+                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = unpack_op16x2(ws[e]);
+                                v[8 * q + 2 * e] = __float_as_uint(fmaf(s_x, f.x, __uint_as_float(v[8 * q + 2 * e])));
+                                v[8 * q + 2 * e + 1] = __float_as_uint(fmaf(s_x, f.y, __uint_as_float(v[8 * q + 2 * e + 1])));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {     // 4 x 16-byte chunks (8 fp16) of this half row
                         uint4 w;

@@ -432,12 +432,14 @@ int launch_attention_mma(McmHandle* h, const op16_t* qkv, op16_t* out, int b, in
 int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const op16_t* qkv, op16_t* out, int b, int S,
                      int H, cudaStream_t st) {
     if (b <= 0) return MCM_OK;
-    if (h->attn_mma || S > 256) return launch_attention_mma(h, qkv, out, b, S, H, st);
+    if (h->attn_mma || S > kAtcMaxS) return launch_attention_mma(h, qkv, out, b, S, H, st);
     AtcParams p{};
     p.b = b;
     p.S = S;
     p.H = H;
-    p.keys_pad = (S + 15) / 16 * 16;
+    p.keys_pad = atc_keys_pad(S);
+    p.n_extra = S > 256 ? S - 256 : 0;
+    p.qkv = qkv;
     p.units_per_item = (S + 127) / 128;
     p.scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
     p.out = out;
@@ -457,7 +459,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     const int items = b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    if (h->attn_split && p.keys_pad <= 208) {
+    if (h->attn_split && p.keys_pad <= 208 && p.n_extra == 0) {
         const int smem2 = ats_smem_bytes(p.keys_pad);
         static int attr_smem2 = 0;
         if (smem2 > attr_smem2) {
@@ -820,9 +822,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         h->attn_mma = e && e[0] == '1';
         const char* e3 = getenv("MCM_ATTN_SPLIT");
         h->attn_split = e3 && e3[0] == '1';
-        if (h->S <= 256) {
+        if (h->S <= kAtcMaxS) {
             MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
-            MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, (h->S + 15) / 16 * 16));
+            MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, atc_keys_pad(h->S)));
         }
     }
 #undef MCM_TRY
@@ -1159,10 +1161,10 @@ int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t
     if (!h || !qkv || !o) return fail(h, MCM_EINVAL, "mcm_dbg_attention: NULL argument");
     if (b <= 0 || S <= 0 || H <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_attention: b, S, H must be positive");
     CUtensorMap tq, tkv;
-    if (S <= 256 && !h->attn_mma) {
+    if (S <= kAtcMaxS && !h->attn_mma) {
         int rc;
         if ((rc = make_tmap(h, &tq, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 128))) return rc;
-        if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, (S + 15) / 16 * 16))) return rc;
+        if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, atc_keys_pad(S)))) return rc;
     }
     return launch_attention(h, tq, tkv, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
                             static_cast<cudaStream_t>(stream));

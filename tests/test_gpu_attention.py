@@ -6,8 +6,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("b,S,H", [(1, 50, 2), (3, 197, 4), (2, 197, 12), (2, 257, 16), (1, 16, 1), (1, 17, 1)])
+@pytest.mark.parametrize("b,S,H", [(1, 50, 2), (3, 197, 4), (2, 197, 12), (2, 257, 16), (1, 16, 1), (1, 17, 1),
+                                   (1, 255, 2), (2, 256, 3), (3, 257, 2), (37, 257, 16), (1, 258, 2), (1, 290, 1)])
 def test_attention(engine_factory, b, S, H):
+    """S <= 256: tensor-core keys only; S = 257 (ViT-L/14): 256 tensor-core keys + the extra key on the CUDA
+    cores; S > 257 falls back to the warp-level mma.sync kernel."""
     eng, _, _ = engine_factory("tiny", 5, 8)
     g = torch.Generator(device="cuda").manual_seed(S * 13 + H)
     D = H * 64
@@ -21,3 +24,26 @@ def test_attention(engine_factory, b, S, H):
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     assert err <= 3e-2, err     # fp16 probabilities / fp16 output rounding
+
+
+def test_attention_extra_key_dominates(engine_factory):
+    """ViT-L/14 geometry with the 257th key carrying the row maximum for most rows and a distinctive value row:
+    exercises the extra-key branch of the row max, the row sum and the O update."""
+    eng, _, _ = engine_factory("tiny", 5, 8)
+    b, S, H = 3, 257, 4
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(99)
+    qkv = torch.randn(b, S, 3 * D, device="cuda", generator=g)
+    qkv[:, :, :2 * D] *= 1.2
+    q_mean = qkv[:, :, :D].mean(dim=1)                       # [b, D]
+    qkv[:, 256, D:2 * D] = 6.0 * q_mean / q_mean.norm(dim=-1, keepdim=True) + qkv[:, 256, D:2 * D]
+    qkv[:, 256, 2 * D:] += 5.0
+    qkv = qkv.reshape(b * S, 3 * D).to(torch.float16)
+    out = eng.dbg_attention(qkv, b, S, H).float().reshape(b, S, H, 64)
+    q, k, v = [t.float().reshape(b, S, H, 64).transpose(1, 2) for t in qkv.split(D, dim=1)]
+    prob = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (prob @ v).transpose(1, 2)
+    torch.cuda.synchronize()
+    assert prob[..., 256].max().item() > 0.5                 # the extra key really matters in this case
+    err = (out - ref).abs().max().item()
+    assert err <= 3e-2, err

@@ -12,7 +12,8 @@ from mcm_b200.engine import McmEngine  # noqa: E402
 
 cfg = synth.CFGS["tiny"]
 eng = McmEngine.from_state_dict(synth.synth_vision_state_dict(cfg, 5), cfg, max_batch=4)
-for b, S, H in [(256, 197, 12), (256, 50, 12), (64, 197, 12)]:
+shapes = [tuple(int(v) for v in c.split(",")) for c in os.environ.get("SWEEP_SHAPES", "256,197,12;256,50,12;64,197,12;128,257,16").split(";")]
+for b, S, H in shapes:
     qkv = (torch.randn(b * S, 3 * H * 64, device="cuda") * 1.5).to(torch.float16)
     for _ in range(3):
         eng.dbg_attention(qkv, b, S, H)
