@@ -170,6 +170,8 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    global METRIC
+    METRIC = f"images/sec MCM-scored ({args.model}, K={args.K})"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -4,9 +4,12 @@
 //
 // 257 = 256 + 1: a UMMA tile is at most 256 keys wide and two fp32 score buffers of more than 256 columns do
 // not fit the 512 columns of tensor memory, so the ONE key beyond 256 of ViT-L/14 ("extra key") never enters
-// the tensor core: every softmax thread computes its row's score against it with 64 FMAs (q row and the key
-// straight from the QKV buffer in L2), folds it into the row max / row sum, and adds p_extra * v_extra to the
-// O row while draining it.  The 256 other keys take the normal path with keys_pad = 256.
+// the tensor core: every softmax thread computes its row's score against it with 64 FMAs (its q row from the Q
+// tile, the key from a small "x box": the producer also loads rows 256.. of q / k / v, 8 rows x 128 B each, with
+// every item), folds it into the row max / row sum, and adds p_extra * v_extra to the O row while draining it.
+// (Reading q / k / v of that token from global memory instead put ~5 k cycles of load latency on every unit.)  The 256 other keys take the normal path with keys_pad = 256.  Likewise the one
+// QUERY row beyond 256 does not get a (1 / 128 full) third unit: warp 10 computes it on the CUDA cores from the
+// K / V tiles already in shared memory (257 x 64 FMAs twice per item, hidden behind the two real units).
 //
 // Persistent CTAs (one per SM) walk over (image, head) items; every item is cut into 128-query-row
 // units.  Warp roles:
@@ -39,22 +42,25 @@
 #include <cuda.h>
 #include "ptx.cuh"
 
+#ifndef MCM_ATC_SINGLE_PASS
+#define MCM_ATC_SINGLE_PASS 0   // 1: one TMEM pass per score row with a lazily updated reference maximum (see atc_rescale_p)
+#endif
 #ifndef MCM_ATC_PIPE
 #define MCM_ATC_PIPE 0   // 1: software-pipeline the pass-2 TMEM loads (measured slower: more registers, no MUFU gain)
 #endif
 
 namespace mcm {
 
-constexpr int kAtcThreads = 320;
+constexpr int kAtcThreads = 352;          // 11 warps: TMA, MMA, 2 x 4 softmax, tail-row warp (idle unless S > 256)
 constexpr int kAtcQStages = 3;
 constexpr int kAtcQBytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kAtcStagingBytes = 8 * 32 * 128; // 8 softmax warps x 32 rows x 64 fp16
+constexpr int kAtcXBytes = 3 * 1024;           // per K/V stage: q | k | v of tokens 256..263 (8 rows x 128 B each)
 
 struct AtcParams {
     int b, S, H, keys_pad;   // keys_pad: min(S, 256) rounded up to 16
     int n_extra;             // S - 256 if S > 256 (0 or 1): keys handled outside the tensor core
-    const op16_t* qkv;       // the fused QKV buffer the tensor maps cover (read directly for the extra key)
-    int units_per_item;      // ceil(S / 128)
+    int units_per_item;      // ceil(min(S, 256) / 128)
     float scale_log2e;       // dh^-0.5 * log2(e)
     op16_t* out;
     long long* trace;        // debug builds (-DMCM_ATC_TRACE): per-phase clock64 stamps of CTA 0, else unused
@@ -75,7 +81,7 @@ constexpr int kAtcMaxS = 257;   // 256 tensor-core keys + 1 extra key
 __host__ __device__ inline int atc_keys_pad(int S) { return ((S < 256 ? S : 256) + 15) / 16 * 16; }
 
 __host__ __device__ inline int atc_smem_bytes(int keys_pad) {
-    return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
+    return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + 2 * kAtcXBytes + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
 }
 
 // ---- extra tcgen05 PTX ----
@@ -110,14 +116,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
-// dot product of two 64-element fp16 rows (128 B each, 16-byte aligned), fp32 accumulation
-__device__ __forceinline__ float atc_dot64(const op16_t* __restrict__ a, const op16_t* __restrict__ b) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(a);
-    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+// dot product of two 64-element fp16 rows in shared memory, fp32 accumulation: row a is row `swz` (mod 8) of a
+// 128-byte-swizzled tile (16-byte chunk j sits at j ^ swz), row b is row 0 of its tile (not swizzled)
+__device__ __forceinline__ float atc_dot64(uint32_t a, int swz, uint32_t b) {
     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const uint4 x = __ldg(a4 + j), y = __ldg(b4 + j);
+        const uint4 x = lds_v4u(a + ((j ^ swz) << 4)), y = lds_v4u(b + (j << 4));
         const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -169,15 +174,38 @@ __device__ __forceinline__ void atc_chunk_exp(const uint32_t (&v)[32], int k0, i
     tmem_st_32x32b_x16(t_p, pk);
 }
 
+// Single-pass softmax (MCM_ATC_SINGLE_PASS): every 32-key chunk is read from tensor memory ONCE.  The row keeps
+// a reference maximum m (scaled units) that is an actual score of the row; a chunk whose maximum exceeds m + 8
+// raises it and the probabilities already written (fp16 in TMEM) and the partial sums are multiplied by
+// 2^(m_old - m_new) -- rare: a later key has to beat every earlier one by a factor of 256.  All probabilities
+// stay <= 2^8 (exact in fp16's range), the row's largest one is >= 1, and O / rowsum is independent of m.
+// f: this lane's factor (1 for rows that keep their maximum); n16: number of 16-column P chunks written so far.
+__device__ __forceinline__ void atc_rescale_p(uint32_t t_p, int n16, float f) {
+    tmem_st_wait();
+    for (int i = 0; i < n16; ++i) {
+        uint32_t pk[16];
+        tmem_ld_32x32b_x16(t_p + 16 * i, pk);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const float2 v = unpack_op16x2(pk[e]);
+            pk[e] = pack_op16x2(v.x * f, v.y * f);
+        }
+        tmem_st_32x32b_x16(t_p + 16 * i, pk);
+    }
+    tmem_st_wait();
+}
+
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                         const AtcParams p) {
+                         const __grid_constant__ CUtensorMap tmap_x, const AtcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kv_bytes = p.keys_pad * 128;                       // one K or V tile
     uint8_t* s_q = smem;                                         // [kAtcQStages][16 KB]
     uint8_t* s_kv = smem + kAtcQStages * kAtcQBytes;             // [2][K | V]
-    uint8_t* s_stage = s_kv + 4 * kv_bytes;                      // [8 warps][32 rows][128 B]
+    uint8_t* s_xbox = s_kv + 4 * kv_bytes;                          // [2][q | k | v of tokens 256..263]  (S > 256 only)
+    uint8_t* s_stage = s_xbox + 2 * kAtcXBytes;                     // [8 warps][32 rows][128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kAtcStagingBytes);
     uint64_t* q_full = bars;                       // [3]
     uint64_t* q_empty = bars + kAtcQStages;        // [3]
@@ -198,9 +226,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
-        for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        if (p.n_extra > 0) tma_prefetch_desc(&tmap_x);
+        // with an extra key the softmax warps read their q rows from the Q tile and k / v of the extra token from the
+        // x box: they release the Q stage and the K / V stage together with the MMA thread's commits
+        for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], p.n_extra > 0 ? 5 : 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], p.n_extra > 0 ? 2 + 4 * upi : 1);   // + tail-row warp + 4 softmax warps per unit
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
         }
@@ -223,10 +254,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const int row0 = img * p.S;
                 const int kvs = ic & 1;
                 mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes);
+                mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes + (p.n_extra > 0 ? kAtcXBytes : 0));
                 uint8_t* sk = s_kv + kvs * 2 * kv_bytes;
                 tma_load_2d(sk, &tmap_kv, &kv_full[kvs], D + h * 64, row0);
                 tma_load_2d(sk + kv_bytes, &tmap_kv, &kv_full[kvs], 2 * D + h * 64, row0);
+                if (p.n_extra > 0) {
+                    uint8_t* sx = s_xbox + kvs * kAtcXBytes;
+#pragma unroll
+                    for (int part = 0; part < 3; ++part)
+                        tma_load_2d(sx + part * 1024, &tmap_x, &kv_full[kvs], part * D + h * 64, row0 + 256);
+                }
                 for (int mt = 0; mt < upi; ++mt, ++uc) {
                     const int qs = uc % kAtcQStages;
                     mbar_wait(&q_empty[qs], ((uc / kAtcQStages) & 1) ^ 1);
@@ -283,6 +320,114 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 }
             }
         }
+    } else if (warp == 10) {
+        // ===== tail-row warp: query rows >= 256 (ViT-L/14: the one row 256) against all S keys, on the CUDA cores =====
+        if (p.n_extra > 0) {
+            const float c = p.scale_log2e;
+            uint32_t ic = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+                const int img = item / p.H, h = item - img * p.H;
+                const int kvs = ic & 1;
+                const uint32_t sk = smem_u32(s_kv + kvs * 2 * kv_bytes);
+                const uint32_t sv = sk + kv_bytes;
+                const uint32_t sx = smem_u32(s_xbox + kvs * kAtcXBytes);      // q | k | v of tokens 256.., row e swizzled by e
+                mbar_wait(&kv_full[kvs], (ic >> 1) & 1);
+                for (int r = 256; r < p.S; ++r) {
+                    // the query row, fp32, replicated in every lane
+                    float q[64];
+                    {
+                        const int e0 = r - 256;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 w = lds_v4u(sx + e0 * 128 + ((j ^ e0) << 4));
+                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = unpack_op16x2(ws[e]);
+                                q[8 * j + 2 * e] = f.x;
+                                q[8 * j + 2 * e + 1] = f.y;
+                            }
+                        }
+                    }
+                    // scores: lane owns keys lane + 32 t (t < 8) from the swizzled K tile, plus (lane t' of the
+                    // extra keys) key 256 + t' from global memory
+                    float sc[9];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int k = lane + 32 * t;
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 w = lds_v4u(sk + k * 128 + ((j ^ (k & 7)) << 4));
+                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = unpack_op16x2(ws[e]);
+                                a0 = fmaf(q[8 * j + 2 * e], f.x, a0);
+                                a1 = fmaf(q[8 * j + 2 * e + 1], f.y, a1);
+                            }
+                        }
+                        sc[t] = a0 + a1;
+                    }
+                    sc[8] = -INFINITY;
+                    if (lane < p.n_extra) {
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 w = lds_v4u(sx + 1024 + lane * 128 + ((j ^ lane) << 4));
+                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = unpack_op16x2(ws[e]);
+                                a0 = fmaf(q[8 * j + 2 * e], f.x, a0);
+                                a1 = fmaf(q[8 * j + 2 * e + 1], f.y, a1);
+                            }
+                        }
+                        sc[8] = a0 + a1;
+                    }
+                    float mx = sc[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) mx = fmaxf(mx, sc[t]);
+                    mx = warp_max(mx);
+                    const float mc = mx * c;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {     // probabilities rounded to fp16 like the P operand of the tensor-core path
+                        const float pr = ex2_approx(fmaf(sc[t], c, -mc));       // 2^-inf = 0 for the unused extra slots
+                        sum += pr;
+                        sc[t] = unpack_op16x2(pack_op16x2(pr, 0.f)).x;
+                    }
+                    sum = warp_sum(sum);
+                    // O row: lane owns head dims 2 lane, 2 lane + 1
+                    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+#pragma unroll 8
+                        for (int l = 0; l < 32; ++l) {
+                            const int k = l + 32 * t;
+                            const float pk = __shfl_sync(0xffffffffu, sc[t], l);
+                            uint32_t w;
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sv + k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + (lane & 3) * 4));
+                            const float2 f = unpack_op16x2(w);
+                            o0 = fmaf(pk, f.x, o0);
+                            o1 = fmaf(pk, f.y, o1);
+                        }
+                    }
+                    for (int e = 0; e < p.n_extra; ++e) {
+                        const float pk = __shfl_sync(0xffffffffu, sc[8], e);
+                        uint32_t w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sx + 2048 + e * 128 + (((lane >> 2) ^ e) << 4) + (lane & 3) * 4));
+                        const float2 f = unpack_op16x2(w);
+                        o0 = fmaf(pk, f.x, o0);
+                        o1 = fmaf(pk, f.y, o1);
+                    }
+                    const float inv = 1.0f / sum;
+                    reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(img) * p.S + r) * D + h * 64)[lane] = pack_op16x2(o0 * inv, o1 * inv);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&kv_empty[kvs]);     // this warp is done with the K / V stage
+            }
+        }
     } else {
         // ===== softmax / epilogue groups =====
         const int g = (warp - 2) >> 2;       // group = TMEM buffer
@@ -313,17 +458,81 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             // the extra key (ViT-L/14's 257th token): this row's raw score against it, on the CUDA cores,
             // while the tensor core is still busy with Q K^T of the other 256
             float s_x = 0.f;
-            const op16_t* kv_x = nullptr;
-            if (p.n_extra > 0 && warp_valid) {
-                const size_t ld = static_cast<size_t>(3) * D;
-                kv_x = p.qkv + (static_cast<size_t>(img) * p.S + S_tc) * ld + D + h * 64;     // k of the extra token; v at + D
-                const int row = wrow0 + lane;
-                if (row < p.S) s_x = atc_dot64(p.qkv + (static_cast<size_t>(img) * p.S + row) * ld + h * 64, kv_x);
-            }
+            const uint32_t sx = smem_u32(s_xbox + (iu & 1) * kAtcXBytes);     // q | k | v of the extra token: row 0 of each 1 KB box
             mbar_wait(&s_full[g], j & 1);
+            if (p.n_extra > 0) {
+                // S ready: the MMA thread has seen this unit's Q tile and the item's K / V stage land; observing the
+                // same (completed) phases here makes the TMA writes visible to this warp
+                mbar_wait(&q_full[u % kAtcQStages], (u / kAtcQStages) & 1);
+                mbar_wait(&kv_full[iu & 1], (iu >> 1) & 1);
+                if (warp_valid)
+                    s_x = atc_dot64(smem_u32(s_q + (u % kAtcQStages) * kAtcQBytes) + (quad * 32 + lane) * 128, lane & 7, sx + 1024);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&q_empty[u % kAtcQStages]);
+            }
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 0);       // S ready
             tcgen05_fence_after();
             float row_sum = 1.f;
+#if MCM_ATC_SINGLE_PASS
+            if (warp_valid) {
+                float m = -INFINITY;            // reference maximum, scaled (raw score * c)
+                float sum0 = 0.f, sum1 = 0.f;
+                for (int ch = 0; ch < nfull; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                    tmem_ld_wait();
+                    float cm = atc_chunk_max(v, ch * 32, S_tc, -INFINITY);
+                    if (ch == 0 && p.n_extra > 0) cm = fmaxf(cm, s_x);
+                    cm *= c;
+                    const bool raise = cm > m + 8.0f;
+                    if (__any_sync(0xffffffffu, raise)) {
+                        const float f = raise ? ex2_approx(m - cm) : 1.0f;     // m = -inf (first chunk): f = 0, nothing to scale
+                        if (ch > 0) atc_rescale_p(t_s, ch, f);
+                        sum0 *= f;
+                        sum1 *= f;
+                        if (raise) m = cm;
+                    }
+                    atc_chunk_exp(v, ch * 32, S_tc, c, m, sum0, sum1, t_s + ch * 16);
+                }
+                if (rem16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
+                    tmem_ld_wait();
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (nfull * 32 + e < S_tc) cm = fmaxf(cm, __uint_as_float(v[e]));
+                    if (nfull == 0 && p.n_extra > 0) cm = fmaxf(cm, s_x);
+                    cm *= c;
+                    const bool raise = cm > m + 8.0f;
+                    if (__any_sync(0xffffffffu, raise)) {
+                        const float f = raise ? ex2_approx(m - cm) : 1.0f;
+                        if (nfull > 0) atc_rescale_p(t_s, nfull, f);
+                        sum0 *= f;
+                        sum1 *= f;
+                        if (raise) m = cm;
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k0 = nfull * 32 + 2 * e;
+                        const float p0 = (k0 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -m)) : 0.f;
+                        const float p1 = (k0 + 1 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -m)) : 0.f;
+                        sum0 += p0;
+                        sum1 += p1;
+                        pk[e] = pack_op16x2(p0, p1);
+                    }
+                    tmem_st_32x32b_x8(t_s + nfull * 16, pk);
+                }
+                tmem_st_wait();
+                row_sum = sum0 + sum1;
+                if (p.n_extra > 0) {   // s_x becomes the probability of the extra key, rounded like the P operand
+                    const float px = ex2_approx(fmaf(s_x, c, -m));
+                    row_sum += px;
+                    s_x = unpack_op16x2(pack_op16x2(px, 0.f)).x;
+                }
+            }
+#else
             if (warp_valid) {
                 // ---- pass 1: row max over the S valid keys (only the last chunk can hold padded keys);
                 //      TMEM loads are issued two chunks at a time so their latencies overlap ----
@@ -399,6 +608,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     s_x = unpack_op16x2(pack_op16x2(px, 0.f)).x;
                 }
             }
+#endif
             tcgen05_fence_before();
             __syncwarp();
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 2);       // pass 2 done
@@ -416,10 +626,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     tmem_ld_32x32b_x32(t_s + 128 + hc * 32, v);
                     tmem_ld_wait();
                     if (p.n_extra > 0) {   // O += p_extra * v_extra (warp-uniform addresses: broadcast loads)
-                        const uint4* vx = reinterpret_cast<const uint4*>(kv_x + D + hc * 32);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const uint4 w = __ldg(vx + q);
+                            const uint4 w = lds_v4u(sx + 2048 + ((hc * 4 + q) << 4));
                             const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -444,7 +653,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tcgen05_fence_before();
             __syncwarp();
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 4);       // O drained
-            if (lane == 0) mbar_arrive(&s_free[g]);     // TMEM buffer may be overwritten by the next QK^T
+            if (lane == 0) {
+                mbar_arrive(&s_free[g]);                            // TMEM buffer may be overwritten by the next QK^T
+                if (p.n_extra > 0) mbar_arrive(&kv_empty[iu & 1]);  // this warp is done with the x box of the K / V stage
+            }
             if (warp_valid) {
                 const int cq = lane & 7;
 #pragma unroll

@@ -97,7 +97,7 @@ struct McmHandle {
     float* x_cls = nullptr;                                   // [pad128(max_batch), D] CLS rows of the last layer
     float *t_ln = nullptr, *t_feat = nullptr, *t_logit = nullptr;   // tail scratch: [max_batch, D | P | K]
     CUtensorMap tm_patches, tm_xh, tm_attn, tm_hid;
-    CUtensorMap tm_qkv_q, tm_qkv_kv;   // attention: 128-row Q boxes / keys_pad-row K,V boxes over the fused QKV buffer
+    CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
     bool attn_split = false;           // env MCM_ATTN_SPLIT=1: two threads per query row (16 softmax warps), keys_pad <= 208
     bool cls_shortcut = true;
@@ -322,7 +322,7 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
         const bool use_tma = resid == out && (force >= 0 ? force != 0 : K <= 1024);
         if (use_tma) epi = EPI_BIAS_RESID_F32_LN_TMA;
     }
-    if (f16_out) {
+    if (f16_out && MCM_GEMM_F16_TMA_STORE) {
         int rc = make_tmap_epi(h, &tout, out, M, N, false, bn / 4);
         if (rc) return rc;
     } else if (epi == EPI_BIAS_RESID_F32_LN_TMA) {
@@ -429,8 +429,8 @@ int launch_attention_mma(McmHandle* h, const op16_t* qkv, op16_t* out, int b, in
 }
 
 // tq / tkv: tensor maps over the fused QKV buffer with 128-row and keys_pad-row boxes
-int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const op16_t* qkv, op16_t* out, int b, int S,
-                     int H, cudaStream_t st) {
+int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tx, const op16_t* qkv, op16_t* out,
+                     int b, int S, int H, cudaStream_t st) {
     if (b <= 0) return MCM_OK;
     if (h->attn_mma || S > kAtcMaxS) return launch_attention_mma(h, qkv, out, b, S, H, st);
     AtcParams p{};
@@ -439,8 +439,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     p.H = H;
     p.keys_pad = atc_keys_pad(S);
     p.n_extra = S > 256 ? S - 256 : 0;
-    p.qkv = qkv;
-    p.units_per_item = (S + 127) / 128;
+    p.units_per_item = ((S < 256 ? S : 256) + 127) / 128;   // query rows >= 256 go to the tail-row warp
     p.scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
     p.out = out;
     p.trace = nullptr;
@@ -470,7 +469,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
         h->launches++;
         return MCM_OK;
     }
-    MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, p));
+    MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
 #ifdef MCM_ATC_TRACE
     {
         static int dumped = 0;
@@ -518,11 +517,12 @@ int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T,
 int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st) {
     {
         ProfScope prof(h, MCM_PROF_PATCHIFY, st);
+        const size_t smem = patchify_smem_bytes(h->G, h->cfg.patch);
         if (u8)
-            MCM_CUDA(h, launch_k(patchify_u8_kernel, dim3(b * h->G), dim3(256), 0, st, 1, static_cast<const uint8_t*>(images), h->patches,
+            MCM_CUDA(h, launch_k(patchify_u8_kernel, dim3(b * h->G), dim3(256), smem, st, 1, static_cast<const uint8_t*>(images), h->patches,
                                  h->G, h->cfg.patch, h->Kp, h->norm));
         else
-            MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), 0, st, 1, static_cast<const float*>(images), h->patches,
+            MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), smem, st, 1, static_cast<const float*>(images), h->patches,
                                  h->G, h->cfg.patch, h->Kp));
     }
     h->launches++;
@@ -586,7 +586,7 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
             *pooled_stride = D;
             break;
         }
-        if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
+        if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->tm_qkv_x, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x, h->x, nullptr, 0, 0, st, prod))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, M, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
         // the last layer's output only feeds the pooled post-LN of the tail: no fp16 copy, no statistics
@@ -710,6 +710,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     *out = nullptr;
     if (cfg->patch <= 0 || cfg->image_size <= 0 || cfg->image_size % cfg->patch != 0 || (cfg->patch & 1))
         return fail(nullptr, MCM_EINVAL, "image_size %d must be a multiple of an even patch size (%d)", cfg->image_size, cfg->patch);
+    if (cfg->image_size % 4 != 0 || patchify_smem_bytes(cfg->image_size / cfg->patch, cfg->patch) > 48 * 1024)
+        return fail(nullptr, MCM_EUNSUPPORTED, "image_size %d (multiple of 4) x patch %d: a row of patches must fit 48 KB of shared memory",
+                    cfg->image_size, cfg->patch);
     if (cfg->width <= 0 || cfg->width % 128 != 0 || cfg->width > 1024)
         return fail(nullptr, MCM_EUNSUPPORTED, "width %d must be a multiple of 128, at most 1024", cfg->width);
     if (cfg->heads <= 0 || cfg->width != cfg->heads * 64)
@@ -825,6 +828,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         if (h->S <= kAtcMaxS) {
             MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
             MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, atc_keys_pad(h->S)));
+            MCM_TRY(make_tmap(h, &h->tm_qkv_x, h->qkv, h->m_pad, 3 * D, 8));
         }
     }
 #undef MCM_TRY
@@ -1160,13 +1164,14 @@ int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float*
 int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t S, int32_t H, void* stream) {
     if (!h || !qkv || !o) return fail(h, MCM_EINVAL, "mcm_dbg_attention: NULL argument");
     if (b <= 0 || S <= 0 || H <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_attention: b, S, H must be positive");
-    CUtensorMap tq, tkv;
+    CUtensorMap tq, tkv, tx;
     if (S <= kAtcMaxS && !h->attn_mma) {
         int rc;
         if ((rc = make_tmap(h, &tq, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 128))) return rc;
         if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, atc_keys_pad(S)))) return rc;
+        if ((rc = make_tmap(h, &tx, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 8))) return rc;
     }
-    return launch_attention(h, tq, tkv, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
+    return launch_attention(h, tq, tkv, tx, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
                             static_cast<cudaStream_t>(stream));
 }
 

@@ -31,7 +31,14 @@
 namespace mcm {
 
 constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
-constexpr int kResidBufs = 2;        // TMA residual epilogue: residual chunks in flight per warp
+#ifndef MCM_GEMM_F16_TMA_STORE
+#define MCM_GEMM_F16_TMA_STORE 1   // 1: fp16 outputs leave through a shared-memory staging tile + TMA bulk stores (default)
+                                   // 0: 32-byte row-per-thread stores straight from registers (A/B builds; measured slower)
+#endif
+#ifndef MCM_RESID_BUFS
+#define MCM_RESID_BUFS 2
+#endif
+constexpr int kResidBufs = MCM_RESID_BUFS;   // TMA residual epilogue: residual chunks in flight per warp
 constexpr int kResidWarpBytes = kResidBufs * 4096 + 2048;   // + the fp16 staging tile
 constexpr int kMaxStatsParts = 8;    // LayerNorm fold: partial row statistics per row (width <= 1024: 2 per 256-column tile)
 constexpr int kStgLd = 32;           // fp32 staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
@@ -56,6 +63,7 @@ struct EpiTraits {
 // Shared memory: operand ring + epilogue staging + barriers.  What the epilogue stages decides how many
 // ring stages are left of the 227 KB:
 //   fp16 outputs          16 warps x (32 rows x 128 B) = 64 KB : one TMA bulk store per warp and tile
+//                         [MCM_GEMM_F16_TMA_STORE=0: none, 32-byte row-per-thread stores straight from registers]
 //   fp32, LSU             8 warps x (32 rows x 128 B)  = 32 KB : transpose tile (EPI_BIAS_RESID_F32, EPI_POS_F32, ..._LN)
 //   fp32 + fp16, TMA      8 warps x (2 x 4 KB residual in / fp32 out + 2 KB fp16 out) = 80 KB  (EPI_BIAS_RESID_F32_LN_TMA)
 template <int BLOCK_N, int EPI>
@@ -64,7 +72,7 @@ struct Gemm2Smem {
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagingBytes = T::kF16 ? 16 * (BLOCK_N / 4) * 64 : T::kTmaResid ? 8 * kResidWarpBytes : 32 * 1024;
+    static constexpr int kStagingBytes = T::kF16 ? (MCM_GEMM_F16_TMA_STORE ? 16 * (BLOCK_N / 4) * 64 : 0) : T::kTmaResid ? 8 * kResidWarpBytes : 32 * 1024;
     static constexpr int kBarrierBytes = 512;
     static constexpr int kBudget = 232448 - 1024 /* alignment slack */ - kBarrierBytes - kStagingBytes;
     static constexpr int kStages = (kBudget / kStageBytes) < 8 ? (kBudget / kStageBytes) : 8;
@@ -282,7 +290,46 @@ __device__ __forceinline__ void gemm2_f16_chunk_math(const GemmParams& p, uint32
     }
 }
 
-// One warp's slice of a tile (32 rows x BLOCK_N / 4 columns): math per 32-column chunk, the packed rows are
+// 256-bit global store (one full 32-byte sector per thread)
+__device__ __forceinline__ void stg_256(void* gptr, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(gptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+// One warp's slice of a tile (32 rows x BLOCK_N / 4 columns) WITHOUT shared memory or the TMA unit
+// (MCM_GEMM_F16_TMA_STORE=0 builds): math per 32-column chunk on the row this thread owns, then two 32-byte stores
+// of the packed row straight from registers (every store instruction writes 32 whole sectors).
+// Why it exists, and why it is not the default (clock64 trace build, K = 768 projections, cycles per 256 x 256 tile):
+//   no epilogue at all 6.16 k (= the UMMA rate) | staging writes only 6.17 k | staging + TMA bulk stores 7.4 k
+//   (the issuer waits for operand data: the bulk stores queue in the TMA unit in front of the operand loads, which
+//   alone already move ~125 B/clk/SM) | direct stores 8.0 k: the operand loads are no longer delayed (data waits
+//   drop from 4.0 k to 1.7 k) but the LSU retires about one 32-byte sector per clock, the 16 warps' stores pile up
+//   behind each other and the epilogue (7.4 k busy) becomes longer than the main loop.
+template <int EPI, int BLOCK_N>
+__device__ __forceinline__ void gemm2_epilogue_slice_f16_direct(const GemmParams& p, uint32_t t_addr, int m_base, int col0, int lane,
+                                                                float rstd, float nmr, uint32_t release_bar) {
+    constexpr int kChunks = BLOCK_N / 128;   // 32-column chunks per slice
+    if (p.dbg_skip & 4) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(release_bar);
+        return;
+    }
+    const int m = m_base + lane;
+    op16_t* orow = static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col0;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        uint32_t pk[16];
+        gemm2_f16_chunk_math<EPI>(p, t_addr + c * 32, col0 + c * 32, lane, rstd, nmr, c + 1 == kChunks ? release_bar : 0u, pk);
+        if (m < p.m_valid && !(p.dbg_skip & 1)) {
+            stg_256(orow + c * 32, pk);
+            stg_256(orow + c * 32 + 16, pk + 8);
+        }
+    }
+}
+
+// The same slice through a staging tile + TMA (MCM_GEMM_F16_TMA_STORE builds): the packed rows are
 // written into the warp's staging tile in the TMA swizzle layout of the output box (128-byte rows / SWIZZLE_128B
 // for 64-column slices, 64-byte rows / SWIZZLE_64B for 32-column slices -- conflict-free for a row-per-thread
 // writer) and leave as ONE bulk store per tile; rows beyond the tensor are clipped by the TMA unit.
@@ -373,7 +420,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if constexpr (T::kF16 || T::kTmaResid) tma_prefetch_desc(&tmap_out);
+        if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid) tma_prefetch_desc(&tmap_out);
         if constexpr (T::kTmaResid) tma_prefetch_desc(&tmap_out16);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
@@ -471,7 +518,9 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         if constexpr (T::kF16) {
             const int slice = ew >> 2;                  // which quarter of the tile's columns this warp drains
             constexpr int kSliceCols = BLOCK_N / 4;
+#if MCM_GEMM_F16_TMA_STORE
             const uint32_t stg = smem_u32(staging + ew * (kSliceCols * 64));
+#endif
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m_blk = tile / p.n_tiles;
                 const int n_blk = tile - m_blk * p.n_tiles;
@@ -509,7 +558,11 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + slice * kSliceCols;
                 const uint32_t release_bar = mapa_shared(smem_u32(&tmem_empty[as]), 0);   // the pair leader's barrier
                 if (m_base < p.m_valid) {
+#if MCM_GEMM_F16_TMA_STORE
                     gemm2_epilogue_slice_f16<EPI, BLOCK_N>(p, &tmap_out, stg, t_row, m_base, col_base, lane, rstd, nmr, release_bar);
+#else
+                    gemm2_epilogue_slice_f16_direct<EPI, BLOCK_N>(p, t_row, m_base, col_base, lane, rstd, nmr, release_bar);
+#endif
                 } else {
                     tcgen05_fence_before();
                     __syncwarp();
@@ -713,7 +766,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
     }
 
-    if constexpr (T::kF16 || T::kTmaResid) {
+    if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid) {
         if (warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores must have completed before the CTA exits
     }
     __syncwarp();

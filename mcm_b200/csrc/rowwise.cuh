@@ -168,29 +168,47 @@ fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ gam
 // Patch gather ("im2col" of the stride = kernel = patch conv, HF:148-154,209-210):
 //   images f32 [b, 3, H, W] NCHW  ->  patches fp16 [b * G * G, Kp],  column = c * p * p + i * p + j
 // (the flattening order of the conv weight [D, 3, p, p]); columns >= 3 p^2 (K padding) are never
-// written and stay zero.  One CTA copies the 3 * p image rows that make up one row of G patches:
-// reads are contiguous 224-float image rows, writes are p-element runs.
+// written and stay zero.  One CTA converts the 3 * p image rows that make up one row of G patches:
+// 16-byte streaming reads of contiguous image rows, the fp16 patch rows are assembled in shared memory
+// (G * 3 p^2 halves, <= 43 KB) and leave as contiguous 8-byte runs (3 p^2 fp16 = 6 p^2 bytes per patch).
+__host__ __device__ inline int patchify_smem_bytes(int G, int p) { return G * 3 * p * p * 2; }
+
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp) {
+    extern __shared__ __align__(16) uint8_t patchify_smem[];
+    op16_t* tile = reinterpret_cast<op16_t*>(patchify_smem);      // [G][3 p^2]
     pdl_launch_dependents();
     pdl_wait();
     const int W = G * p;
+    const int kpatch = 3 * p * p;
     const int gy = blockIdx.x % G;
     const int b = blockIdx.x / G;
-    const int half_w = W >> 1;
-    const int n = 3 * p * half_w;  // float2 items in this patch row
+    const int quarter_w = W >> 2;                  // W = 224: a multiple of 4 for every CLIP patch size
+    const int n = 3 * p * quarter_w;               // float4 items of this patch row
     const float* src_img = img + static_cast<size_t>(b) * 3 * W * W;
-    op16_t* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int xh = t % half_w;
-        const int ci = t / half_w;  // c * p + i
+        const int xq = t % quarter_w;
+        const int ci = t / quarter_w;  // c * p + i
         const int i = ci % p;
         const int c = ci / p;
-        const int x = xh * 2;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(src_img + (static_cast<size_t>(c) * W + gy * p + i) * W + x));
-        const int gx = x / p;
-        const int j = x - gx * p;
-        *reinterpret_cast<uint32_t*>(dst_row + static_cast<size_t>(gx) * Kp + (c * p + i) * p + j) = pack_op16x2(v.x, v.y);
+        const int x = xq * 4;
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src_img + (static_cast<size_t>(c) * W + gy * p + i) * W + x));
+        const float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {           // x is even and p is even: a pixel pair never straddles two patches
+            const int gx = (x + e) / p;
+            const int j = (x + e) - gx * p;
+            *reinterpret_cast<uint32_t*>(tile + gx * kpatch + ci * p + j) = pack_op16x2(vs[e], vs[e + 1]);
+        }
+    }
+    __syncthreads();
+    op16_t* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
+    const int run8 = kpatch >> 2;                  // 8-byte items per patch
+    const uint2* t2 = reinterpret_cast<const uint2*>(tile);
+    for (int t = threadIdx.x; t < G * run8; t += blockDim.x) {
+        const int gx = t / run8;
+        const int o = t - gx * run8;
+        *reinterpret_cast<uint2*>(dst_row + static_cast<size_t>(gx) * Kp + 4 * o) = t2[t];
     }
 }
 
@@ -201,41 +219,53 @@ patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int
 // fp32 arithmetic in torchvision's order (true divisions), so the fp16 patch rows are bit-identical to
 // patchify_kernel run on the fp32 tensor the reference's DataLoader would have produced -- at a quarter of the
 // PCIe / HBM bytes.  One CTA handles the p image rows of one row of G patches: reads are contiguous 3 W-byte
-// pixel rows (16-byte vector loads when W * 3 is a multiple of 16), writes are fp16 pairs.
+// pixel rows (12 bytes = 4 pixels per thread), the patch rows are assembled in shared memory like patchify_kernel.
 struct NormConst { float mean[3], std[3]; };
 
 __global__ void __launch_bounds__(256)
 patchify_u8_kernel(const uint8_t* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp, const NormConst nc) {
+    extern __shared__ __align__(16) uint8_t patchify_smem[];
+    op16_t* tile = reinterpret_cast<op16_t*>(patchify_smem);      // [G][3 p^2]
     pdl_launch_dependents();
     pdl_wait();
     const int W = G * p;
+    const int kpatch = 3 * p * p;
     const int gy = blockIdx.x % G;
     const int b = blockIdx.x / G;
     const int row_bytes = 3 * W;                  // one pixel row, HWC
     const uint8_t* src = img + (static_cast<size_t>(b) * W + static_cast<size_t>(gy) * p) * row_bytes;
-    op16_t* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
-    // item = 2 horizontally adjacent pixels (6 bytes) of image row i: x is even and p is even, so both land in one patch
-    const int half_w = W >> 1;
-    const int n = p * half_w;
+    // item = 4 horizontally adjacent pixels (12 bytes, 4-byte aligned) of image row i
+    const int quarter_w = W >> 2;
+    const int n = p * quarter_w;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int xh = t % half_w;
-        const int i = t / half_w;
-        const int x = xh * 2;
-        const uint8_t* q = src + static_cast<size_t>(i) * row_bytes + 3 * x;   // 6-byte run, 2-byte aligned
-        const uint16_t w0 = __ldg(reinterpret_cast<const uint16_t*>(q));
-        const uint16_t w1 = __ldg(reinterpret_cast<const uint16_t*>(q + 2));
-        const uint16_t w2 = __ldg(reinterpret_cast<const uint16_t*>(q + 4));
-        const float px0[3] = {static_cast<float>(w0 & 0xff), static_cast<float>(w0 >> 8), static_cast<float>(w1 & 0xff)};
-        const float px1[3] = {static_cast<float>(w1 >> 8), static_cast<float>(w2 & 0xff), static_cast<float>(w2 >> 8)};
-        const int gx = x / p;
-        const int j = x - gx * p;
-        op16_t* d = dst_row + static_cast<size_t>(gx) * Kp + i * p + j;
+        const int xq = t % quarter_w;
+        const int i = t / quarter_w;
+        const int x = xq * 4;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(i) * row_bytes + 3 * x);
+        const uint32_t w[3] = {__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
+        float v[4][3];                            // [pixel][channel], ToTensor + Normalize in torchvision's order
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float a = __fdiv_rn(__fsub_rn(__fdiv_rn(px0[c], 255.0f), nc.mean[c]), nc.std[c]);
-            const float e = __fdiv_rn(__fsub_rn(__fdiv_rn(px1[c], 255.0f), nc.mean[c]), nc.std[c]);
-            *reinterpret_cast<uint32_t*>(d + c * p * p) = pack_op16x2(a, e);
+        for (int k = 0; k < 12; ++k) {
+            const float u = static_cast<float>((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            v[k / 3][k % 3] = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nc.mean[k % 3]), nc.std[k % 3]);
         }
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {          // x is even and p is even: a pixel pair never straddles two patches
+            const int gx = (x + e) / p;
+            const int j = (x + e) - gx * p;
+            op16_t* d = tile + gx * kpatch + i * p + j;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t*>(d + c * p * p) = pack_op16x2(v[e][c], v[e + 1][c]);
+        }
+    }
+    __syncthreads();
+    op16_t* dst_row = patches + (static_cast<size_t>(b) * G * G + static_cast<size_t>(gy) * G) * Kp;
+    const int run8 = kpatch >> 2;
+    const uint2* t2 = reinterpret_cast<const uint2*>(tile);
+    for (int t = threadIdx.x; t < G * run8; t += blockDim.x) {
+        const int gx = t / run8;
+        const int o = t - gx * run8;
+        *reinterpret_cast<uint2*>(dst_row + static_cast<size_t>(gx) * Kp + 4 * o) = t2[t];
     }
 }
 

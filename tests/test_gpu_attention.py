@@ -34,9 +34,9 @@ def test_attention_extra_key_dominates(engine_factory):
     D = H * 64
     g = torch.Generator(device="cuda").manual_seed(99)
     qkv = torch.randn(b, S, 3 * D, device="cuda", generator=g)
-    qkv[:, :, :2 * D] *= 1.2
-    q_mean = qkv[:, :, :D].mean(dim=1)                       # [b, D]
-    qkv[:, 256, D:2 * D] = 6.0 * q_mean / q_mean.norm(dim=-1, keepdim=True) + qkv[:, 256, D:2 * D]
+    u = torch.randn(D, device="cuda", generator=g)
+    qkv[:, :, :D] += u                                        # every query shares a component with ...
+    qkv[:, 256, D:2 * D] = 1.5 * u                            # ... the key of token 256: logit ~ 0.125 * 1.5 * 64 = 12
     qkv[:, 256, 2 * D:] += 5.0
     qkv = qkv.reshape(b * S, 3 * D).to(torch.float16)
     out = eng.dbg_attention(qkv, b, S, H).float().reshape(b, S, H, 64)
@@ -45,5 +45,29 @@ def test_attention_extra_key_dominates(engine_factory):
     ref = (prob @ v).transpose(1, 2)
     torch.cuda.synchronize()
     assert prob[..., 256].max().item() > 0.5                 # the extra key really matters in this case
+    err = (out - ref).abs().max().item()
+    assert err <= 3e-2, err
+
+
+@pytest.mark.parametrize("S", [197, 257, 50])
+def test_attention_late_maximum(engine_factory, S):
+    """Rows whose maximum sits in a late key chunk and beats everything before it by far more than 2^8
+    (twice, in two different chunks): the case a lazily updated softmax reference maximum must rescale for."""
+    eng, _, _ = engine_factory("tiny", 5, 8)
+    b, H = 2, 3
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(7 + S)
+    qkv = torch.randn(b, S, 3 * D, device="cuda", generator=g)
+    u = torch.randn(D, device="cuda", generator=g)
+    qkv[:, :, :D] = 0.3 * qkv[:, :, :D] + u
+    qkv[:, S // 2, D:2 * D] = 3.0 * u        # logit ~ 0.125 * 64 * 3 = 24 above the rest
+    qkv[:, S - 7, D:2 * D] = 6.0 * u         # and another 24 above that one
+    qkv[:, S // 2, 2 * D:] -= 3.0
+    qkv[:, S - 7, 2 * D:] += 2.0
+    qkv = qkv.reshape(b * S, 3 * D).to(torch.float16)
+    out = eng.dbg_attention(qkv, b, S, H).float().reshape(b, S, H, 64)
+    q, k, v = [t.float().reshape(b, S, H, 64).transpose(1, 2) for t in qkv.split(D, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2)
+    torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     assert err <= 3e-2, err
