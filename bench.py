@@ -270,6 +270,24 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e2e / float(te.item())
 
+    # ---------------- end-to-end from decoded uint8 pixels (uint8 ingest: ToTensor + Normalize fused on the device) ----------------
+    del host
+    host8 = torch.randint(0, 256, (n_host * B, cfg.image_size, cfg.image_size, 3), dtype=torch.uint8).pin_memory()
+    eng.score_stream_host_u8(host8[: 2 * B], batch=B)
+    barrier()
+    t0 = time.perf_counter()
+    done = 0
+    while done < n_e2e:
+        cur = min(n_e2e - done, host8.shape[0])
+        eng.score_stream_host_u8(host8[:cur], batch=B)
+        done += cur
+    torch.cuda.synchronize(dev)
+    te8 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te8, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * n_e2e / float(te8.item())
+    del host8
+
     # ---------------- full last layer (no CLS shortcut), same timing protocol ----------------
     eng.set_cls_shortcut(False)
     for i in range(2):
@@ -333,6 +351,9 @@ def main():
                        "precision": "fp16 tensor-core operands, fp32 accumulate / residual / LayerNorm / softmax / tail"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
                     "d2h_bytes_per_step": B * 4},
+            "e2e_uint8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2,
+                          "d2h_bytes_per_step": B * 4,
+                          "note": "same call with decoded uint8 HWC pixels (mcm_score_stream_host_u8): ToTensor + Normalize on the device"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05, all GEMMs of a step)",

@@ -306,6 +306,9 @@ __device__ __forceinline__ void stg_256(void* gptr, const uint32_t* r) {
 //   alone already move ~125 B/clk/SM) | direct stores 8.0 k: the operand loads are no longer delayed (data waits
 //   drop from 4.0 k to 1.7 k) but the LSU retires about one 32-byte sector per clock, the 16 warps' stores pile up
 //   behind each other and the epilogue (7.4 k busy) becomes longer than the main loop.
+// A third variant -- staging tiles drained by two dedicated store warps with coalesced 128-bit LSU stores, so that
+// the math warps never wait on a store -- measured 7.7-8.5 k: two warps cannot keep 64 KB per tile moving through
+// the LSU, four more warps do not fit the register file next to 16 epilogue warps.  Bulk stores stay the default.
 template <int EPI, int BLOCK_N>
 __device__ __forceinline__ void gemm2_epilogue_slice_f16_direct(const GemmParams& p, uint32_t t_addr, int m_base, int col0, int lane,
                                                                 float rstd, float nmr, uint32_t release_bar) {
