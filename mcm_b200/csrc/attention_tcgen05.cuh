@@ -137,8 +137,15 @@ __device__ __forceinline__ float atc_dot64(uint32_t a, int swz, uint32_t b) {
 // running max over one 32-key chunk of a score row (keys k0 .. k0 + 31; keys >= S are padding)
 __device__ __forceinline__ float atc_chunk_max(const uint32_t (&v)[32], int k0, int S, float mx) {
     if (k0 + 32 <= S) {
+        // a tree instead of one running maximum: 3-input max instructions, dependency depth 5 instead of 16
+        float t[11];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+        for (int i = 0; i < 10; ++i)
+            t[i] = fmaxf(fmaxf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
+        t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+        const float r0 = fmaxf(fmaxf(t[0], t[1]), t[2]), r1 = fmaxf(fmaxf(t[3], t[4]), t[5]);
+        const float r2 = fmaxf(fmaxf(t[6], t[7]), t[8]), r3 = fmaxf(fmaxf(t[9], t[10]), mx);
+        mx = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3));
     } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e)
