@@ -127,6 +127,22 @@ int mcm_score_u8(McmHandle* h, const uint8_t* images_dev, int32_t b, float T, in
 int mcm_score_stream_host_u8(McmHandle* h, const uint8_t* images_host, int64_t n, int32_t batch, float T,
                              int32_t score_kind, float* scores_host);
 
+/* Resize(image_size) + CenterCrop(image_size), the FIRST two steps of the reference preprocess (utils/train_eval_util.py:
+ * 29-31; run there by torchvision on PIL images in the DataLoader workers), on the device for a batch of decoded RGB
+ * images of different sizes: image i is uint8 [hs[i], ws[i], 3] (HWC) at byte offsets[i] of the packed device buffer
+ * `src_dev`; offsets / hs / ws are HOST arrays of n entries.  dst_dev is uint8 [n, image_size, image_size, 3], ready
+ * for mcm_score_u8 / mcm_image_features_u8, and bit-identical to torchvision.transforms.Resize + CenterCrop on PIL
+ * images (Pillow's antialiased two-pass fixed-point bilinear resampler, torchvision's size / crop-offset rules).
+ * Asynchronous on `stream`; the per-call resampling tables are built on the host and copied with the launch. */
+int mcm_resize_crop_u8(McmHandle* h, const uint8_t* src_dev, const int64_t* offsets_host, const int32_t* hs_host,
+                       const int32_t* ws_host, int32_t n, uint8_t* dst_dev, void* stream);
+
+/* The host half of mcm_resize_crop_u8 for ONE h x w image (no device needed): the fixed-point resampling tables of the
+ * `size` output columns / rows that survive the crop, `[first source index, count, k[ksize]]` per output, ksize2 =
+ * {ksize_h, ksize_v}; table_h / table_v hold `cap` int32 each.  Lets the CPU tests check the planner against Pillow. */
+int mcm_dbg_resize_tables(int32_t h, int32_t w, int32_t size, int32_t* ksize2, int32_t* table_h, int32_t* table_v,
+                          int32_t cap);
+
 /* Number of kernels of this library launched on the handle's device since the last reset
  * (bench.py reports it as `gpu_launches`). */
 int64_t mcm_launch_count(const McmHandle* h);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mcm_image_features_u8": (C.c_int, [_H, _P, C.c_int32, _P, _P]),
     "mcm_score_u8": (C.c_int, [_H, _P, C.c_int32, C.c_float, C.c_int32, _P, _P]),
     "mcm_score_stream_host_u8": (C.c_int, [_H, _P, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
+    "mcm_resize_crop_u8": (C.c_int, [_H, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, _P, _P]),
+    "mcm_dbg_resize_tables": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P, _P, C.c_int32]),
     "mcm_launch_count": (C.c_int64, [_H]),
     "mcm_reset_launch_count": (None, [_H]),
     "mcm_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),

@@ -30,6 +30,7 @@
 #include "attention_tcgen05_split.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
+#include "resize.cuh"
 #include "rowwise.cuh"
 #include "tail.cuh"
 
@@ -111,6 +112,14 @@ struct McmHandle {
     int64_t scores_cap = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+    // resize + crop ingest: double-buffered plan staging (pinned host -> device), one event per slot
+    uint8_t* rc_host[2] = {nullptr, nullptr};
+    uint8_t* rc_dev[2] = {nullptr, nullptr};
+    size_t rc_cap[2] = {0, 0};
+    cudaEvent_t rc_ev[2] = {nullptr, nullptr};
+    int rc_slot = 0;
+    int rc_smem_attr = 0;
 
     int64_t launches = 0;
 
@@ -852,6 +861,11 @@ void mcm_destroy(McmHandle* h) {
     fr(h->img_buf[0]); fr(h->img_buf[1]); fr(h->scores_buf);
     fr(h->x_cls); fr(h->t_ln); fr(h->t_feat); fr(h->t_logit);
     for (int i = 0; i < 2; ++i) {
+        fr(h->rc_dev[i]);
+        if (h->rc_host[i]) cudaFreeHost(h->rc_host[i]);
+        if (h->rc_ev[i]) cudaEventDestroy(h->rc_ev[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
@@ -986,6 +1000,69 @@ int mcm_score_stream_host(McmHandle* h, const float* images_host, int64_t n, int
 int mcm_score_stream_host_u8(McmHandle* h, const uint8_t* images_host, int64_t n, int32_t batch, float T, int32_t kind,
                              float* scores_host) {
     return score_stream_host_any(h, images_host, true, n, batch, T, kind, scores_host);
+}
+
+int mcm_resize_crop_u8(McmHandle* h, const uint8_t* src, const int64_t* offsets, const int32_t* hs, const int32_t* ws, int32_t n,
+                       uint8_t* dst, void* stream) {
+    if (!h) return MCM_EINVAL;
+    if (n == 0) return MCM_OK;
+    if (n < 0 || !src || !offsets || !hs || !ws || !dst) return fail(h, MCM_EINVAL, "mcm_resize_crop_u8: bad argument");
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int size = h->cfg.image_size;
+    RcPlan plan;
+    if (const char* msg = rc_plan(offsets, hs, ws, n, size, plan)) return fail(h, MCM_EUNSUPPORTED, "mcm_resize_crop_u8: %s", msg);
+    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t b_img = up16(plan.images.size() * sizeof(RcImage)), b_tile = up16(plan.tiles.size() * sizeof(RcTile));
+    const size_t b_pool = up16(plan.pool.size() * sizeof(int32_t)), total = b_img + b_tile + b_pool;
+    const int slot = h->rc_slot;
+    h->rc_slot ^= 1;
+    if (!h->rc_ev[slot]) MCM_CUDA(h, cudaEventCreateWithFlags(&h->rc_ev[slot], cudaEventDisableTiming));
+    MCM_CUDA(h, cudaEventSynchronize(h->rc_ev[slot]));      // the copy that last used this slot's host buffer has finished
+    if (total > h->rc_cap[slot]) {
+        if (h->rc_host[slot]) cudaFreeHost(h->rc_host[slot]);
+        if (h->rc_dev[slot]) cudaFree(h->rc_dev[slot]);
+        h->rc_host[slot] = nullptr;
+        h->rc_dev[slot] = nullptr;
+        h->rc_cap[slot] = 0;
+        const size_t cap = total * 2;
+        MCM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->rc_host[slot]), cap));
+        int rc = dev_alloc(h, &h->rc_dev[slot], cap, false);
+        if (rc) return rc;
+        h->rc_cap[slot] = cap;
+    }
+    uint8_t* hb = h->rc_host[slot];
+    memcpy(hb, plan.images.data(), plan.images.size() * sizeof(RcImage));
+    memcpy(hb + b_img, plan.tiles.data(), plan.tiles.size() * sizeof(RcTile));
+    memcpy(hb + b_img + b_tile, plan.pool.data(), plan.pool.size() * sizeof(int32_t));
+    uint8_t* db = h->rc_dev[slot];
+    MCM_CUDA(h, cudaMemcpyAsync(db, hb, total, cudaMemcpyHostToDevice, st));
+    MCM_CUDA(h, cudaEventRecord(h->rc_ev[slot], st));
+    if (plan.max_smem > h->rc_smem_attr) {
+        MCM_CUDA(h, cudaFuncSetAttribute(resize_crop_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRcMaxSmem));
+        h->rc_smem_attr = kRcMaxSmem;
+    }
+    resize_crop_u8_kernel<<<static_cast<unsigned>(plan.tiles.size()), 256, plan.max_smem, st>>>(
+        src, reinterpret_cast<const RcImage*>(db), reinterpret_cast<const RcTile*>(db + b_img),
+        reinterpret_cast<const int32_t*>(db + b_img + b_tile), dst, size);
+    MCM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCM_OK;
+}
+
+int mcm_dbg_resize_tables(int32_t h, int32_t w, int32_t size, int32_t* ksize2, int32_t* table_h, int32_t* table_v, int32_t cap) {
+    if (h <= 0 || w <= 0 || size <= 0 || !ksize2 || !table_h || !table_v) return MCM_EINVAL;
+    RcPlan plan;
+    const int64_t off = 0;
+    if (rc_plan(&off, &h, &w, 1, size, plan)) return MCM_EUNSUPPORTED;
+    const RcImage& im = plan.images[0];
+    ksize2[0] = im.ksize_h;
+    ksize2[1] = im.ksize_v;
+    const int nh = size * (2 + im.ksize_h), nv = size * (2 + im.ksize_v);
+    if (nh > cap || nv > cap) return MCM_ENOMEM;
+    memcpy(table_h, plan.pool.data() + im.coef_h, nh * sizeof(int32_t));
+    memcpy(table_v, plan.pool.data() + im.coef_v, nv * sizeof(int32_t));
+    return MCM_OK;
 }
 
 int mcm_set_normalization(McmHandle* h, const float* mean3, const float* std3) {

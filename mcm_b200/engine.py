@@ -208,6 +208,48 @@ class McmEngine:
                                                            C.c_void_p(out.ctypes.data)))
         return out
 
+    def resize_crop_u8(self, images) -> torch.Tensor:
+        """``CenterCrop(S)(Resize(S)(img))`` of the reference preprocess (``utils/train_eval_util.py:29-31``) for a list
+        of decoded RGB images of arbitrary sizes (uint8 ``[h, w, 3]`` ndarrays / CPU tensors), on the device:
+        returns a uint8 ``[n, S, S, 3]`` device tensor, bit-identical to torchvision on PIL images, ready for
+        :meth:`score_u8`.  The images are packed into one pinned buffer and cross PCIe once, undecimated."""
+        arrs = [np.ascontiguousarray(np.asarray(im)) for im in images]
+        for a in arrs:
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("resize_crop_u8 needs uint8 [h, w, 3] (RGB, HWC) images")
+        n = len(arrs)
+        S = self.cfg.image_size
+        out = torch.empty((n, S, S, 3), dtype=torch.uint8, device=self.device)
+        if n == 0:
+            return out
+        sizes = np.array([a.size for a in arrs], dtype=np.int64)
+        offsets = np.zeros(n, dtype=np.int64)
+        offsets[1:] = np.cumsum((sizes[:-1] + 15) // 16 * 16)          # 16-byte aligned starts
+        total = int(offsets[-1] + sizes[-1])
+        packed = torch.empty((total,), dtype=torch.uint8).pin_memory()
+        pk = packed.numpy()
+        for a, o in zip(arrs, offsets):
+            pk[o:o + a.size] = a.reshape(-1)
+        src = packed.to(self.device, non_blocking=True)
+        hs = np.array([a.shape[0] for a in arrs], dtype=np.int32)
+        ws = np.array([a.shape[1] for a in arrs], dtype=np.int32)
+        self._check(self._lib.mcm_resize_crop_u8(
+            self._h, _ptr(src), offsets.ctypes.data_as(C.POINTER(C.c_int64)), hs.ctypes.data_as(C.POINTER(C.c_int32)),
+            ws.ctypes.data_as(C.POINTER(C.c_int32)), n, _ptr(out), self._stream()))
+        src.record_stream(torch.cuda.current_stream(self.device))
+        return out
+
+    def score_images(self, images, T: float = 1.0, score: str = "MCM") -> torch.Tensor:
+        """Decoded RGB images of arbitrary sizes -> scores: the WHOLE reference preprocess (Resize, CenterCrop, ToTensor,
+        Normalize) and the scoring path on the device.  Returns a device tensor ``[n]``."""
+        images = list(images)
+        parts = []
+        for s0 in range(0, len(images), self.max_batch):
+            parts.append(self.score_u8(self.resize_crop_u8(images[s0:s0 + self.max_batch]), T=T, score=score))
+        if not parts:
+            return torch.empty((0,), dtype=torch.float32, device=self.device)
+        return torch.cat(parts)
+
     def score_stream_host(self, images_host, batch: Optional[int] = None, T: float = 1.0,
                           score: str = "MCM") -> np.ndarray:
         """Whole evaluation stream from HOST memory (the loop of ``utils/detection_util.py:220-249``):

@@ -193,3 +193,32 @@ def test_uint8_ingest_is_bit_identical_to_fp32_path(tiny_net):
 def eng_sd(tiny_net_fixture):
     from mcm_b200 import synth
     return synth.synth_vision_state_dict(tiny_net_fixture[1], 5)
+
+
+def test_resize_crop_on_device_matches_oracle(tiny_net):
+    """mcm_resize_crop_u8: Resize(224) + CenterCrop(224) of a ragged batch of decoded images on the device, bit-identical
+    to the oracle restatement of torchvision + Pillow (pinned to them in tests/test_oracle_golden.py), and the whole
+    preprocess + scoring chain equal to scoring the tensor the reference's DataLoader would have produced."""
+    from oracle import clip_mcm_oracle as O
+    from oracle import pil_resize_oracle as R
+    from oracle.make_golden_resize import image
+    net, cfg, bank = tiny_net
+    eng = net.engine
+    sizes = [(375, 500), (500, 375), (224, 224), (224, 300), (301, 224), (100, 160), (333, 1000), (1500, 431), (64, 64),
+             (227, 229), (375, 500), (2000, 3008), (37, 1000), (500, 375)]
+    imgs = [image(h, w, i) for i, (h, w) in enumerate(sizes)]
+    want = np.stack([R.resize_center_crop_u8(im) for im in imgs])
+    got = eng.resize_crop_u8(imgs)
+    assert got.shape == (len(imgs), 224, 224, 3) and got.dtype == torch.uint8
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # twice more: the plan staging is double-buffered and reused
+    np.testing.assert_array_equal(eng.resize_crop_u8(imgs[:3]).cpu().numpy(), want[:3])
+    np.testing.assert_array_equal(eng.resize_crop_u8(imgs[3:9]).cpu().numpy(), want[3:9])
+    scores = eng.score_images(imgs).cpu().numpy()
+    ref = eng.score(O.preprocess_u8(want).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(scores, ref)
+    assert eng.resize_crop_u8([]).shape == (0, 224, 224, 3)
+    with pytest.raises(ValueError):
+        eng.resize_crop_u8([np.zeros((10, 10), np.uint8)])
+    with pytest.raises(RuntimeError):
+        eng.resize_crop_u8([np.zeros((20000, 224, 3), np.uint8)])      # down-scaling factor beyond the tile budget

@@ -54,3 +54,59 @@ def test_oracle_preprocess_matches_torchvision():
     got = O.preprocess_u8(u8)
     assert got.dtype == torch.float32 and got.shape == (3, 3, 224, 224)
     assert torch.equal(got, ref)
+
+
+RESIZE_SIZES = [(375, 500), (500, 375), (224, 224), (224, 300), (301, 224), (225, 224), (100, 160), (160, 100),
+                (333, 1000), (1500, 431), (64, 64), (227, 229), (900, 1200)]
+
+
+def test_resize_oracle_matches_torchvision():
+    """oracle.pil_resize_oracle == CenterCrop(224)(Resize(224)(pil_image)) executed by torchvision + Pillow themselves
+    (the first two steps of the reference val_preprocess, utils/train_eval_util.py:29-31), bit for bit, over
+    down-scaling, up-scaling, both orientations, odd crop offsets and the no-op size."""
+    PIL = pytest.importorskip("PIL.Image")
+    T = pytest.importorskip("torchvision.transforms")
+    from oracle import pil_resize_oracle as R
+    tf = T.Compose([T.Resize(224), T.CenterCrop(224)])
+    rng = np.random.default_rng(3)
+    for h, w in RESIZE_SIZES:
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        ref = np.asarray(tf(PIL.fromarray(img)))
+        got = R.resize_center_crop_u8(img)
+        assert got.shape == (224, 224, 3) and got.dtype == np.uint8
+        np.testing.assert_array_equal(got, ref, err_msg=f"{h}x{w}")
+
+
+def test_resize_planner_tables_match_oracle():
+    """The host half of mcm_resize_crop_u8 (C++, csrc/resize.cuh: size / crop rules + Pillow's coefficient tables in
+    fixed point) against the oracle restatement -- runs without a GPU through mcm_dbg_resize_tables."""
+    import ctypes as C
+    from mcm_b200 import _lib
+    from oracle import pil_resize_oracle as R
+    lib = _lib.load()
+    for h, w in RESIZE_SIZES + [(3000, 4000), (4000, 3000), (1, 7)]:
+        cap = 224 * (2 + 600)
+        th, tv, ks = np.zeros(cap, np.int32), np.zeros(cap, np.int32), (C.c_int32 * 2)()
+        assert lib.mcm_dbg_resize_tables(h, w, 224, ks, C.c_void_p(th.ctypes.data), C.c_void_p(tv.ctypes.data), cap) == 0
+        th = th[:224 * (2 + ks[0])].reshape(224, -1)
+        tv = tv[:224 * (2 + ks[1])].reshape(224, -1)
+        nh, nw = R.resized_size(h, w)
+        top, left = R.crop_offsets(nh, nw)
+        bh, ch = R.precompute_coeffs(w, nw)
+        bv, cv = R.precompute_coeffs(h, nh)
+        np.testing.assert_array_equal(th[:, :2], bh[left:left + 224], err_msg=f"{h}x{w} bounds_h")
+        np.testing.assert_array_equal(th[:, 2:], ch[left:left + 224], err_msg=f"{h}x{w} kk_h")
+        np.testing.assert_array_equal(tv[:, :2], bv[top:top + 224], err_msg=f"{h}x{w} bounds_v")
+        np.testing.assert_array_equal(tv[:, 2:], cv[top:top + 224], err_msg=f"{h}x{w} kk_v")
+
+
+def test_resize_oracle_matches_golden_digests(golden_dir):
+    """Same pin without Pillow / torchvision: SHA-1 digests of their outputs on seeded images, made here by
+    oracle/make_golden_resize.py."""
+    import hashlib
+    from oracle import pil_resize_oracle as R
+    from oracle.make_golden_resize import image
+    z = np.load(os.path.join(golden_dir, "resize_crop_pil.npz"))
+    for i, ((h, w), want) in enumerate(zip(z["sizes"], z["sha1"])):
+        got = R.resize_center_crop_u8(image(int(h), int(w), i))
+        assert hashlib.sha1(got.tobytes()).hexdigest() == str(want), f"{h}x{w}"
