@@ -1067,8 +1067,9 @@ int mcm_dbg_resize_tables(int32_t h, int32_t w, int32_t size, int32_t* ksize2, i
 
 int mcm_set_normalization(McmHandle* h, const float* mean3, const float* std3) {
     if (!h || !mean3 || !std3) return fail(h, MCM_EINVAL, "mcm_set_normalization: NULL argument");
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 3; ++c)      // validate everything before touching the state
         if (!(std3[c] > 0.f)) return fail(h, MCM_EINVAL, "std[%d] must be positive (got %g)", c, (double)std3[c]);
+    for (int c = 0; c < 3; ++c) {
         h->norm.mean[c] = mean3[c];
         h->norm.std[c] = std3[c];
     }

@@ -133,7 +133,7 @@ inline const char* rc_plan(const int64_t* offsets, const int32_t* hs, const int3
                 ny = cv[last * stride] + cv[last * stride + 1] - y0;
                 if (ny * size * 3 <= kRcMaxSmem || nr == 1) break;
             }
-            if (ny * size * 3 > kRcMaxSmem) return "source image too large for the resampling tile (down-scaling factor above ~45)";
+            if (ny * size * 3 > kRcMaxSmem) return "source image too large for the resampling tile (down-scaling factor above ~70)";
             plan.tiles.push_back(RcTile{i, r0, nr, y0, ny});
             if (ny * size * 3 > plan.max_smem) plan.max_smem = ny * size * 3;
             r0 += nr;

@@ -233,10 +233,32 @@ class McmEngine:
         src = packed.to(self.device, non_blocking=True)
         hs = np.array([a.shape[0] for a in arrs], dtype=np.int32)
         ws = np.array([a.shape[1] for a in arrs], dtype=np.int32)
-        self._check(self._lib.mcm_resize_crop_u8(
-            self._h, _ptr(src), offsets.ctypes.data_as(C.POINTER(C.c_int64)), hs.ctypes.data_as(C.POINTER(C.c_int32)),
-            ws.ctypes.data_as(C.POINTER(C.c_int32)), n, _ptr(out), self._stream()))
+        self.resize_crop_u8_packed(src, offsets, hs, ws, out=out)
         src.record_stream(torch.cuda.current_stream(self.device))
+        return out
+
+    def resize_crop_u8_packed(self, src: torch.Tensor, offsets, hs, ws, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """:meth:`resize_crop_u8` for images already packed in one uint8 DEVICE buffer: image ``i`` is
+        ``[hs[i], ws[i], 3]`` at byte ``offsets[i]`` of ``src`` (``offsets`` / ``hs`` / ``ws``: host integer sequences)."""
+        if not torch.is_tensor(src) or src.dtype != torch.uint8 or src.device != self.device or not src.is_contiguous():
+            raise ValueError(f"src must be a contiguous uint8 tensor on {self.device}")
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        hs = np.ascontiguousarray(hs, dtype=np.int32)
+        ws = np.ascontiguousarray(ws, dtype=np.int32)
+        n = int(offsets.shape[0])
+        if hs.shape != (n,) or ws.shape != (n,):
+            raise ValueError("offsets, hs and ws must have one entry per image")
+        if n and (offsets.min() < 0 or int((offsets + hs.astype(np.int64) * ws * 3).max()) > src.numel()):
+            raise ValueError("an image lies outside the packed source buffer")
+        S = self.cfg.image_size
+        if out is None:
+            out = torch.empty((n, S, S, 3), dtype=torch.uint8, device=self.device)
+        elif out.dtype != torch.uint8 or out.device != self.device or not out.is_contiguous() or out.numel() < n * S * S * 3:
+            raise ValueError("out must be a contiguous uint8 device tensor of at least n * S * S * 3 elements")
+        if n:
+            self._check(self._lib.mcm_resize_crop_u8(
+                self._h, _ptr(src), offsets.ctypes.data_as(C.POINTER(C.c_int64)), hs.ctypes.data_as(C.POINTER(C.c_int32)),
+                ws.ctypes.data_as(C.POINTER(C.c_int32)), n, _ptr(out), self._stream()))
         return out
 
     def score_images(self, images, T: float = 1.0, score: str = "MCM") -> torch.Tensor:

@@ -98,6 +98,8 @@ def test_resize_planner_tables_match_oracle():
         np.testing.assert_array_equal(th[:, 2:], ch[left:left + 224], err_msg=f"{h}x{w} kk_h")
         np.testing.assert_array_equal(tv[:, :2], bv[top:top + 224], err_msg=f"{h}x{w} bounds_v")
         np.testing.assert_array_equal(tv[:, 2:], cv[top:top + 224], err_msg=f"{h}x{w} kk_v")
+    # a down-scaling factor beyond the shared-memory tile budget is refused, not mis-computed
+    assert lib.mcm_dbg_resize_tables(20000, 20000, 224, ks, C.c_void_p(th.ctypes.data), C.c_void_p(tv.ctypes.data), cap) == _lib.EUNSUPPORTED
 
 
 def test_resize_oracle_matches_golden_digests(golden_dir):
