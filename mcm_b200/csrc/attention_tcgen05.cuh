@@ -8,8 +8,8 @@
 // tile, the key from a small "x box": the producer also loads rows 256.. of q / k / v, 8 rows x 128 B each, with
 // every item), folds it into the row max / row sum, and adds p_extra * v_extra to the O row while draining it.
 // (Reading q / k / v of that token from global memory instead put ~5 k cycles of load latency on every unit.)  The 256 other keys take the normal path with keys_pad = 256.  Likewise the one
-// QUERY row beyond 256 does not get a (1 / 128 full) third unit: warp 10 computes it on the CUDA cores from the
-// K / V tiles already in shared memory (257 x 64 FMAs twice per item, hidden behind the two real units).
+// QUERY row beyond 256 does not get a (1 / 128 full) third unit: warp 10 computes it with warp-level mma.sync tiles
+// from the K / V tiles already in shared memory, hidden behind the two real units.
 //
 // Persistent CTAs (one per SM) walk over (image, head) items; every item is cut into 128-query-row
 // units.  Warp roles:
@@ -328,10 +328,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
         }
     } else if (warp == 10) {
-        // ===== tail-row warp: query rows >= 256 (ViT-L/14: the one row 256) against all S keys, on the CUDA cores =====
+        // ===== tail-row warp: query rows >= 256 (ViT-L/14: the one row 256) against all S keys =====
+        // Warp-level mma.sync (m16n8k16) on the K / V tiles already in shared memory: the row is row 0 of a 16-row
+        // tile whose other rows are zero, flash-style over 64-key chunks like attention_mma.cuh, then the extra
+        // keys from the x box.  (A CUDA-core version of this warp cost ~2.8 k issue slots per item on the SM
+        // sub-partition it shares with two softmax warps; this one ~1 k.)
         if (p.n_extra > 0) {
             const float c = p.scale_log2e;
+            const int tq = lane & 3;
+            const bool row_lane = (lane >> 2) == 0;      // lanes 0..3 hold row 0 of the tile
             uint32_t ic = 0;
+            auto lds32 = [](uint32_t a) { uint32_t w; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(a)); return w; };
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
                 const int img = item / p.H, h = item - img * p.H;
                 const int kvs = ic & 1;
@@ -340,96 +347,108 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const uint32_t sx = smem_u32(s_xbox + kvs * kAtcXBytes);      // q | k | v of tokens 256.., row e swizzled by e
                 mbar_wait(&kv_full[kvs], (ic >> 1) & 1);
                 for (int r = 256; r < p.S; ++r) {
-                    // the query row, fp32, replicated in every lane
-                    float q[64];
-                    {
-                        const int e0 = r - 256;
+                    const int e0 = r - 256;
+                    // A fragments: row 0 = the query row (x box, q part), rows 1..15 = 0
+                    uint32_t qf[4][4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint4 w = lds_v4u(sx + e0 * 128 + ((j ^ e0) << 4));
-                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const int col = ks * 16 + tq * 2;
+                        qf[ks][0] = row_lane ? lds32(sx + e0 * 128 + ((((col >> 3)) ^ e0) << 4) + (col & 7) * 2) : 0u;
+                        qf[ks][2] = row_lane ? lds32(sx + e0 * 128 + ((((col >> 3) + 1) ^ e0) << 4) + (col & 7) * 2) : 0u;
+                        qf[ks][1] = qf[ks][3] = 0u;
+                    }
+                    float o[8][4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = unpack_op16x2(ws[e]);
-                                q[8 * j + 2 * e] = f.x;
-                                q[8 * j + 2 * e + 1] = f.y;
+                    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+                    float m0 = -INFINITY, l0 = 0.f;
+                    for (int kc = 0; kc < p.keys_pad; kc += 64) {       // S > 256: keys_pad = 256, every chunk is full and valid
+                        float sc[8][4];
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+                        for (int np = 0; np < 4; ++np) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                // ldmatrix x4: (keys 0-7, dh 0-7), (keys 0-7, dh 8-15), (keys 8-15, dh 0-7), (keys 8-15, dh 8-15)
+                                const int kr = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                                const int ch = ks * 2 + ((lane >> 3) & 1);                 // 16-byte chunk of the key row
+                                uint32_t kf[4];
+                                ldmatrix_x4(kf, sk + kr * 128 + ((ch ^ (kr & 7)) << 4));
+                                mma_op16_16816(sc[np * 2], qf[ks], kf[0], kf[1]);
+                                mma_op16_16816(sc[np * 2 + 1], qf[ks], kf[2], kf[3]);
+                            }
+                        }
+                        float cm = -INFINITY;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) cm = fmaxf(cm, fmaxf(sc[nt][0], sc[nt][1]));
+                        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+                        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+                        const float mn = fmaxf(m0, cm);
+                        const float a = ex2_approx((m0 - mn) * c);                         // 0 on the first chunk
+                        m0 = mn;
+                        const float ms = mn * c;
+                        float rs = 0.f;
+                        uint32_t pf[4][4];
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            const float p0 = ex2_approx(fmaf(sc[nt][0], c, -ms)), p1 = ex2_approx(fmaf(sc[nt][1], c, -ms));
+                            rs += p0 + p1;
+                            pf[nt >> 1][(nt & 1) * 2] = pack_op16x2(p0, p1);
+                            pf[nt >> 1][(nt & 1) * 2 + 1] = 0u;                            // rows 8..15 of the tile
+                        }
+                        l0 = l0 * a + rs;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { o[i][0] *= a; o[i][1] *= a; }
+#pragma unroll
+                        for (int kp = 0; kp < 4; ++kp) {
+#pragma unroll
+                            for (int dp = 0; dp < 4; ++dp) {
+                                // ldmatrix x4 trans: (keys 0-7, dh 0-7), (keys 8-15, dh 0-7), (keys 0-7, dh 8-15), (keys 8-15, dh 8-15)
+                                const int vr = kc + kp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                                const int ch = dp * 2 + (lane >> 4);
+                                uint32_t vf[4];
+                                ldmatrix_x4_trans(vf, sv + vr * 128 + ((ch ^ (vr & 7)) << 4));
+                                mma_op16_16816(o[dp * 2], pf[kp], vf[0], vf[1]);
+                                mma_op16_16816(o[dp * 2 + 1], pf[kp], vf[2], vf[3]);
                             }
                         }
                     }
-                    // scores: lane owns keys lane + 32 t (t < 8) from the swizzled K tile, plus (lane t' of the
-                    // extra keys) key 256 + t' from global memory
-                    float sc[9];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int k = lane + 32 * t;
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint4 w = lds_v4u(sk + k * 128 + ((j ^ (k & 7)) << 4));
-                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = unpack_op16x2(ws[e]);
-                                a0 = fmaf(q[8 * j + 2 * e], f.x, a0);
-                                a1 = fmaf(q[8 * j + 2 * e + 1], f.y, a1);
-                            }
-                        }
-                        sc[t] = a0 + a1;
-                    }
-                    sc[8] = -INFINITY;
-                    if (lane < p.n_extra) {
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint4 w = lds_v4u(sx + 1024 + lane * 128 + ((j ^ lane) << 4));
-                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = unpack_op16x2(ws[e]);
-                                a0 = fmaf(q[8 * j + 2 * e], f.x, a0);
-                                a1 = fmaf(q[8 * j + 2 * e + 1], f.y, a1);
-                            }
-                        }
-                        sc[8] = a0 + a1;
-                    }
-                    float mx = sc[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) mx = fmaxf(mx, sc[t]);
-                    mx = warp_max(mx);
-                    const float mc = mx * c;
-                    float sum = 0.f;
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) {     // probabilities rounded to fp16 like the P operand of the tensor-core path
-                        const float pr = ex2_approx(fmaf(sc[t], c, -mc));       // 2^-inf = 0 for the unused extra slots
-                        sum += pr;
-                        sc[t] = unpack_op16x2(pack_op16x2(pr, 0.f)).x;
-                    }
-                    sum = warp_sum(sum);
-                    // O row: lane owns head dims 2 lane, 2 lane + 1
-                    float o0 = 0.f, o1 = 0.f;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-#pragma unroll 8
-                        for (int l = 0; l < 32; ++l) {
-                            const int k = l + 32 * t;
-                            const float pk = __shfl_sync(0xffffffffu, sc[t], l);
-                            uint32_t w;
-                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sv + k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + (lane & 3) * 4));
-                            const float2 f = unpack_op16x2(w);
-                            o0 = fmaf(pk, f.x, o0);
-                            o1 = fmaf(pk, f.y, o1);
-                        }
-                    }
+                    // the extra keys (tokens 256 + e, x box k / v parts), one at a time
                     for (int e = 0; e < p.n_extra; ++e) {
-                        const float pk = __shfl_sync(0xffffffffu, sc[8], e);
-                        uint32_t w;
-                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sx + 2048 + e * 128 + (((lane >> 2) ^ e) << 4) + (lane & 3) * 4));
-                        const float2 f = unpack_op16x2(w);
-                        o0 = fmaf(pk, f.x, o0);
-                        o1 = fmaf(pk, f.y, o1);
+                        float sx_dot = 0.f;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const int col = ks * 16 + tq * 2;
+                            const float2 q0 = unpack_op16x2(qf[ks][0]), q1 = unpack_op16x2(qf[ks][2]);
+                            const float2 k0 = unpack_op16x2(lds32(sx + 1024 + e * 128 + (((col >> 3) ^ e) << 4) + (col & 7) * 2));
+                            const float2 k1 = unpack_op16x2(lds32(sx + 1024 + e * 128 + ((((col >> 3) + 1) ^ e) << 4) + (col & 7) * 2));
+                            sx_dot = fmaf(q0.x, k0.x, fmaf(q0.y, k0.y, fmaf(q1.x, k1.x, fmaf(q1.y, k1.y, sx_dot))));
+                        }
+                        sx_dot += __shfl_xor_sync(0xffffffffu, sx_dot, 1);
+                        sx_dot += __shfl_xor_sync(0xffffffffu, sx_dot, 2);
+                        const float mn = fmaxf(m0, sx_dot);
+                        const float a = ex2_approx((m0 - mn) * c);
+                        const float px = ex2_approx((sx_dot - mn) * c);
+                        m0 = mn;
+                        l0 = l0 * a + (tq == 0 ? px : 0.f);                                // l0 is summed over the quad below
+                        const float pxr = unpack_op16x2(pack_op16x2(px, 0.f)).x;           // rounded like the P operand
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            const int col = nt * 8 + tq * 2;
+                            const float2 v = unpack_op16x2(lds32(sx + 2048 + e * 128 + (((col >> 3) ^ e) << 4) + (col & 7) * 2));
+                            o[nt][0] = fmaf(pxr, v.x, o[nt][0] * a);
+                            o[nt][1] = fmaf(pxr, v.y, o[nt][1] * a);
+                        }
                     }
-                    const float inv = 1.0f / sum;
-                    reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(img) * p.S + r) * D + h * 64)[lane] = pack_op16x2(o0 * inv, o1 * inv);
+                    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+                    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+                    const float inv = 1.0f / l0;
+                    if (row_lane) {
+                        op16_t* orow = p.out + (static_cast<size_t>(img) * p.S + r) * D + h * 64;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            *reinterpret_cast<uint32_t*>(orow + nt * 8 + tq * 2) = pack_op16x2(o[nt][0] * inv, o[nt][1] * inv);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&kv_empty[kvs]);     // this warp is done with the K / V stage
