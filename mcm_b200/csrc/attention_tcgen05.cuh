@@ -31,9 +31,11 @@
 // Measured (clock64 phase trace of one CTA, ViT-B/16 shape, tools/attn_sweep.py with the -DMCM_ATC_TRACE
 // build): one unit takes ~7.7 k cycles end to end -- row max 1.4 k, exp2 pass 3.1 k (the warp's own
 // instruction stream, MUFU 53 % busy), and ~3.2 k of hand-offs (barrier hops, issuing 13 P.V UMMAs,
-// draining O) -- with two units in flight per SM (TMEM holds two S buffers).  Tried and rejected, all
-// within +-5 %: software-pipelined TMEM loads, two threads per row (attention_tcgen05_split.cuh), one MMA
-// issuer warp per buffer, forcing the two groups out of phase.  96 us per layer call vs 293 us for the
+// draining O) -- with two units in flight per SM (TMEM holds two S buffers).  Tried and rejected: software-
+// pipelined TMEM loads (MCM_ATC_PIPE, +13 %), one pass per row with a lazily raised maximum (MCM_ATC_SINGLE_PASS,
+// +6 %), two threads per row, one MMA issuer warp per buffer, forcing the two groups out of phase (all +-5 %), and
+// moving the 69 rows beyond the first 128 of ViT-B/16 to four mma.sync warps so that an item needs ONE unit (2.2 x
+// slower: a 16-row mma.sync tile over 208 keys takes one warp ~8 k cycles, five of them per item on four warps).  96 us per layer call vs 293 us for the
 // mma.sync kernel; the next step is a third unit in flight (split the keys, rescale O in TMEM).
 //
 // qkv: fp16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)

@@ -27,7 +27,6 @@
 #include "attention_cls.cuh"
 #include "attention_mma.cuh"
 #include "attention_tcgen05.cuh"
-#include "attention_tcgen05_split.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "resize.cuh"
@@ -100,7 +99,6 @@ struct McmHandle {
     CUtensorMap tm_patches, tm_xh, tm_attn, tm_hid;
     CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
-    bool attn_split = false;           // env MCM_ATTN_SPLIT=1: two threads per query row (16 softmax warps), keys_pad <= 208
     bool cls_shortcut = true;
 
     // uint8 ingest: Normalize constants of the reference preprocess (utils/train_eval_util.py:27-28)
@@ -467,17 +465,6 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     const int items = b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    if (h->attn_split && p.keys_pad <= 208 && p.n_extra == 0) {
-        const int smem2 = ats_smem_bytes(p.keys_pad);
-        static int attr_smem2 = 0;
-        if (smem2 > attr_smem2) {
-            MCM_CUDA(h, cudaFuncSetAttribute(attention_tcgen05_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-            attr_smem2 = smem2;
-        }
-        MCM_CUDA(h, launch_k(attention_tcgen05_split_kernel, dim3(grid), dim3(kAtsThreads), smem2, st, 1, tq, tkv, p));
-        h->launches++;
-        return MCM_OK;
-    }
     MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
 #ifdef MCM_ATC_TRACE
     {
@@ -832,8 +819,6 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     {
         const char* e = getenv("MCM_ATTN_MMA");
         h->attn_mma = e && e[0] == '1';
-        const char* e3 = getenv("MCM_ATTN_SPLIT");
-        h->attn_split = e3 && e3[0] == '1';
         if (h->S <= kAtcMaxS) {
             MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
             MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, atc_keys_pad(h->S)));
