@@ -143,6 +143,17 @@ int mcm_resize_crop_u8(McmHandle* h, const uint8_t* src_dev, const int64_t* offs
 int mcm_dbg_resize_tables(int32_t h, int32_t w, int32_t size, int32_t* ksize2, int32_t* table_h, int32_t* table_v,
                           int32_t cap);
 
+/* Mahalanobis baseline, the reference's `--score maha` (utils/detection_util.py:182-207; eval_ood_detection.py:72-79):
+ *   score_i = -max_k( -0.5 (f_i - mu_k)^T P (f_i - mu_k) )   over the K class means mu_k and the shared precision P.
+ * mcm_set_maha takes the statistics pre-whitened by the host (mcm_b200/engine.py does it in fp64): with P = L L^T
+ * (Cholesky), `lt` = L^T [P,P] row-major and `centres` = mu_k L [K,P]; `normalize` mirrors args.normalize (features
+ * L2-normalised first, :197-198).  mcm_maha_score replaces the whole batch loop body (:193-204): the reference's
+ * K-iteration Python loop of two GEMMs per class becomes one whitening GEMM + K squared distances per image.
+ * mcm_dbg_maha_from_features runs the same tail on given [b,P] features (tests). */
+int mcm_set_maha(McmHandle* h, const float* lt, const float* centres, int32_t K, int32_t normalize);
+int mcm_maha_score(McmHandle* h, const float* images_dev, int32_t b, float* scores_dev, void* stream);
+int mcm_dbg_maha_from_features(McmHandle* h, const float* feats_dev, int32_t b, float* scores_dev, void* stream);
+
 /* Number of kernels of this library launched on the handle's device since the last reset
  * (bench.py reports it as `gpu_launches`). */
 int64_t mcm_launch_count(const McmHandle* h);

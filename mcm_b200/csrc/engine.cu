@@ -89,6 +89,11 @@ struct McmHandle {
     float* bank = nullptr;
     int K = 0;
 
+    // Mahalanobis baseline: whitening matrix L^T [P,P], whitened class centres [K,P], scratch [max_batch,P]
+    float *maha_lt = nullptr, *maha_c = nullptr, *maha_g = nullptr;
+    int maha_K = 0;
+    bool maha_normalize = false;
+
     // workspace
     op16_t *patches = nullptr, *xh = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
     float* x = nullptr;                                       // fp32 residual stream; xh = its fp16 copy (GEMM A operand)
@@ -845,6 +850,7 @@ void mcm_destroy(McmHandle* h) {
     fr(h->stage); fr(h->bank); fr(h->patches); fr(h->x); fr(h->xh); fr(h->qkv); fr(h->attn); fr(h->hid);
     fr(h->img_buf[0]); fr(h->img_buf[1]); fr(h->scores_buf);
     fr(h->x_cls); fr(h->t_ln); fr(h->t_feat); fr(h->t_logit);
+    fr(h->maha_lt); fr(h->maha_c); fr(h->maha_g);
     for (int i = 0; i < 2; ++i) {
         fr(h->rc_dev[i]);
         if (h->rc_host[i]) cudaFreeHost(h->rc_host[i]);
@@ -1048,6 +1054,63 @@ int mcm_dbg_resize_tables(int32_t h, int32_t w, int32_t size, int32_t* ksize2, i
     memcpy(table_h, plan.pool.data() + im.coef_h, nh * sizeof(int32_t));
     memcpy(table_v, plan.pool.data() + im.coef_v, nv * sizeof(int32_t));
     return MCM_OK;
+}
+
+namespace {
+// feats [b,P] (un-normalised projected features) -> Mahalanobis scores
+int launch_maha(McmHandle* h, float* feats, int b, float* scores, cudaStream_t st) {
+    ProfScope prof(h, MCM_PROF_TAIL, st);
+    if (h->maha_normalize) MCM_CUDA(h, launch_k(normalize_rows_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, feats, b, h->P));
+    dim3 g1((h->P + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
+    MCM_CUDA(h, launch_k(sgemm_tn_kernel, g1, dim3(256), 0, st, 1, static_cast<const float*>(feats), static_cast<const float*>(h->maha_lt),
+                         h->maha_g, b, h->P, h->P));
+    MCM_CUDA(h, launch_k(maha_min_dist_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, static_cast<const float*>(h->maha_g),
+                         static_cast<const float*>(h->maha_c), h->P, h->maha_K, b, scores));
+    h->launches += h->maha_normalize ? 3 : 2;
+    return MCM_OK;
+}
+}  // namespace
+
+int mcm_set_maha(McmHandle* h, const float* lt, const float* centres, int32_t K, int32_t normalize) {
+    if (!h || !lt || !centres) return fail(h, MCM_EINVAL, "mcm_set_maha: NULL argument");
+    if (K <= 0) return fail(h, MCM_EINVAL, "K must be positive (got %d)", K);
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    MCM_CUDA(h, cudaDeviceSynchronize());
+    auto fr = [](float*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(h->maha_lt); fr(h->maha_c); fr(h->maha_g);
+    h->maha_K = 0;
+    int rc;
+    if ((rc = dev_alloc(h, &h->maha_lt, (size_t)h->P * h->P, false))) return rc;
+    if ((rc = dev_alloc(h, &h->maha_c, (size_t)K * h->P, false))) return rc;
+    if ((rc = dev_alloc(h, &h->maha_g, (size_t)h->cfg.max_batch * h->P, false))) return rc;
+    MCM_CUDA(h, cudaMemcpy(h->maha_lt, lt, (size_t)h->P * h->P * sizeof(float), cudaMemcpyDefault));
+    MCM_CUDA(h, cudaMemcpy(h->maha_c, centres, (size_t)K * h->P * sizeof(float), cudaMemcpyDefault));
+    h->maha_K = K;
+    h->maha_normalize = normalize != 0;
+    return MCM_OK;
+}
+
+int mcm_maha_score(McmHandle* h, const float* images, int32_t b, float* scores, void* stream) {
+    int rc = check_ready(h, b, false);
+    if (rc) return rc;
+    if (h->maha_K <= 0) return fail(h, MCM_ESTATE, "Mahalanobis statistics are not set (call mcm_set_maha)");
+    if (b == 0) return MCM_OK;
+    if (!images || !scores) return fail(h, MCM_EINVAL, "mcm_maha_score: NULL buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* pooled = nullptr;
+    size_t stride = 0;
+    if ((rc = forward_tower(h, images, false, b, st, &pooled, &stride))) return rc;
+    if ((rc = launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, h->t_feat, nullptr, st))) return rc;
+    return launch_maha(h, h->t_feat, b, scores, st);
+}
+
+int mcm_dbg_maha_from_features(McmHandle* h, const float* feats, int32_t b, float* scores, void* stream) {
+    if (!h || !feats || !scores) return fail(h, MCM_EINVAL, "mcm_dbg_maha_from_features: NULL argument");
+    if (h->maha_K <= 0) return fail(h, MCM_ESTATE, "Mahalanobis statistics are not set (call mcm_set_maha)");
+    if (b <= 0 || b > h->cfg.max_batch) return fail(h, MCM_EINVAL, "batch %d outside (0, max_batch=%d]", b, h->cfg.max_batch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MCM_CUDA(h, cudaMemcpyAsync(h->t_feat, feats, (size_t)b * h->P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return launch_maha(h, h->t_feat, b, scores, st);
 }
 
 int mcm_set_normalization(McmHandle* h, const float* mean3, const float* std3) {

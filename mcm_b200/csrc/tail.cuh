@@ -144,8 +144,47 @@ score_rows_kernel(const float* __restrict__ feats, const float* __restrict__ log
     if (lane == 0) scores[img] = out;
 }
 
+// ---- Mahalanobis baseline (reference `--score maha`, utils/detection_util.py:182-207) ----
+//   score_i = -max_k( -0.5 (f_i - mu_k)^T P (f_i - mu_k) ) = 0.5 min_k |g_i - c_k|^2   with P = L L^T, g = f L, c_k = mu_k L:
+// the K quadratic forms of the reference's Python loop (two [b,P]x[P,P] GEMMs per class) become ONE whitening GEMM
+// (g = f L, sgemm_tn_kernel) and K squared distances per image, accumulated as differences (no cancellation).
+// One warp per image; the whitened feature row stays in registers (P <= 1024), the class centres stream from L2.
+__global__ void __launch_bounds__(256)
+maha_min_dist_kernel(const float* __restrict__ g, const float* __restrict__ centres, int P, int K, int b, float* __restrict__ scores) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (img >= b) return;
+    float gr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gr[i] = (lane + 32 * i < P) ? g[static_cast<size_t>(img) * P + lane + 32 * i] : 0.f;
+    float best = INFINITY;
+    for (int k = 0; k < K; ++k) {
+        const float* c = centres + static_cast<size_t>(k) * P;
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (lane + 32 * i < P) {
+                const float z = gr[i] - __ldg(c + lane + 32 * i);
+                d = fmaf(z, z, d);
+            }
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 16);
+        d += __shfl_xor_sync(0xffffffffu, d, 8);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        best = fminf(best, d);
+    }
+    if (lane == 0) scores[img] = 0.5f * best;
+}
+
+
 // bank rows /= ||row||   (utils/detection_util.py:231); one warp per row
 __global__ void normalize_rows_kernel(float* __restrict__ bank, int K, int P) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= K) return;

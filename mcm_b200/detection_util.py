@@ -95,6 +95,69 @@ def get_ood_scores_clip(args, net, loader, test_labels, in_dist=False):
     return torch.cat(parts).cpu().numpy().astype(np.float32, copy=False)[:n_total].copy()
 
 
+def get_mean_prec(args, net, train_loader):
+    """Class-wise means and the shared precision matrix for the Mahalanobis score -- reference signature and results
+    (``utils/detection_util.py:148-180``): features come from the B200 engine, the statistics are the reference's own
+    torch code (fp64 covariance, ``linalg.inv``), INCLUDING that ``classwise_idx`` collects the batch index once per
+    sample (``:166-167``, sic) -- the files it writes under ``args.template_dir`` are interchangeable with the reference's."""
+    import os
+    from collections import defaultdict
+    if not isinstance(net, B200ClipNet):
+        raise TypeError("mcm_b200.get_mean_prec needs a B200ClipNet")
+    eng: McmEngine = net.engine
+    classwise_mean = torch.empty(args.n_cls, args.feat_dim)
+    all_features = []
+    classwise_idx = defaultdict(list)
+    with torch.no_grad():
+        for idx, (images, labels) in enumerate(train_loader):
+            images = images.to(eng.device, non_blocking=True)
+            features = torch.cat([eng.image_features(images[s:s + eng.max_batch]) for s in range(0, images.shape[0], eng.max_batch)]).float()
+            if args.normalize:
+                features /= features.norm(dim=-1, keepdim=True)
+            for label in labels:
+                classwise_idx[label.item()].append(idx)
+            all_features.append(features.cpu())
+    all_features = torch.cat(all_features)
+    for cls in range(args.n_cls):
+        classwise_mean[cls] = torch.mean(all_features[classwise_idx[cls]].float(), dim=0)
+        if args.normalize:
+            classwise_mean[cls] /= classwise_mean[cls].norm(dim=-1, keepdim=True)
+    cov = torch.cov(all_features.T.double())
+    precision = torch.linalg.inv(cov).float()
+    print(f"cond number: {torch.linalg.cond(precision)}")
+    tdir = getattr(args, "template_dir", None)
+    if tdir:
+        os.makedirs(tdir, exist_ok=True)
+        torch.save(classwise_mean, os.path.join(tdir, f"{args.model}_classwise_mean_{args.in_dataset}_{args.max_count}_{args.normalize}.pt"))
+        torch.save(precision, os.path.join(tdir, f"{args.model}_precision_{args.in_dataset}_{args.max_count}_{args.normalize}.pt"))
+    return classwise_mean, precision
+
+
+def get_Mahalanobis_score(args, net, test_loader, classwise_mean, precision, in_dist=True):
+    """Mahalanobis confidence score of every image of ``test_loader`` -- reference signature and return contract
+    (``utils/detection_util.py:182-207``), including its batch rule: with ``in_dist=False`` the loop stops at batch
+    ``len(dataset) // args.batch_size`` (``:191-192``), so a trailing partial batch of an OOD set is not scored."""
+    if not isinstance(net, B200ClipNet):
+        raise TypeError("mcm_b200.get_Mahalanobis_score needs a B200ClipNet")
+    eng: McmEngine = net.engine
+    key = (id(classwise_mean), id(precision), bool(args.normalize))
+    if getattr(eng, "_mcm_maha_key", None) != key:
+        eng.set_maha(classwise_mean, precision, bool(args.normalize))
+        eng._mcm_maha_key = key
+        eng._mcm_maha_refs = (classwise_mean, precision)      # keep the ids alive
+    total_len = len(test_loader.dataset)
+    parts = []
+    for batch_idx, batch in enumerate(test_loader):
+        if (batch_idx >= total_len // args.batch_size) and in_dist is False:
+            break
+        images = (batch[0] if isinstance(batch, (tuple, list)) else batch).to(eng.device, non_blocking=True)
+        for s in range(0, images.shape[0], eng.max_batch):
+            parts.append(eng.maha_score(images[s:s + eng.max_batch]))
+    if not parts:
+        return np.zeros((0,), dtype=np.float32)
+    return torch.cat(parts).cpu().numpy().astype(np.float32, copy=True)
+
+
 def print_measures(log, auroc, aupr, fpr, method_name="Ours", recall_level=0.95):
     """Same report lines as the reference (``:37-45``)."""
     r = int(100 * recall_level)

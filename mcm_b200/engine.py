@@ -291,6 +291,40 @@ class McmEngine:
                                                         C.c_void_p(out.ctypes.data)))
         return out
 
+    # ------------------------------------------------------------ Mahalanobis baseline --
+    def set_maha(self, classwise_mean, precision, normalize: bool = False) -> None:
+        """Install the statistics of the reference's ``--score maha`` (``get_mean_prec``,
+        ``utils/detection_util.py:148-180``): class means ``[K, P]`` and the shared precision matrix ``[P, P]``.
+        The quadratic form only sees the symmetric part of ``precision``; it is factored on the host in fp64
+        (``P = L L^T``) so that the device computes ``0.5 * min_k |f L - mu_k L|^2``."""
+        mean = torch.as_tensor(classwise_mean).detach().cpu().double()
+        prec = torch.as_tensor(precision).detach().cpu().double()
+        P = self.cfg.proj
+        if mean.dim() != 2 or mean.shape[1] != P or tuple(prec.shape) != (P, P):
+            raise ValueError(f"classwise_mean must be [K, {P}] and precision [{P}, {P}]")
+        sym = 0.5 * (prec + prec.T)
+        L, info = torch.linalg.cholesky_ex(sym)
+        if int(info) != 0:
+            raise ValueError("precision matrix is not positive definite (Cholesky failed); Mahalanobis distances are undefined")
+        lt = L.T.contiguous().float()
+        centres = (mean @ L).contiguous().float()
+        self._check(self._lib.mcm_set_maha(self._h, _ptr(lt), _ptr(centres), int(mean.shape[0]), 1 if normalize else 0))
+        self.maha_K = int(mean.shape[0])
+
+    def maha_score(self, images: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One batch of ``get_Mahalanobis_score`` (``utils/detection_util.py:193-204``): device tensor ``[b]``."""
+        b = self._check_images(images)
+        if out is None:
+            out = torch.empty((b,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_maha_score(self._h, _ptr(images.contiguous()), b, _ptr(out), self._stream()))
+        return out[:b]
+
+    def dbg_maha_from_features(self, feats: torch.Tensor) -> torch.Tensor:
+        b = int(feats.shape[0])
+        out = torch.empty((b,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_dbg_maha_from_features(self._h, _ptr(feats.contiguous().float()), b, _ptr(out), self._stream()))
+        return out
+
     # ------------------------------------------------- per-kernel entry points (tests, bench) --
     def dbg_gemm(self, a, w, bias, resid=None, epi: int = 0):
         """epilogue(A[M,K] @ W[N,K]^T) through the tcgen05 GEMM; a, w fp16.  epi 0/1 -> fp16, 2 -> fp32."""

@@ -280,3 +280,62 @@ def flops_per_image(cfg: VisionCfg, K: int) -> float:
     F = cfg.mlp
     return (2.0 * (S - 1) * (3 * p * p) * D + L * (8.0 * S * D * D + 4.0 * S * D * F + 4.0 * S * S * D)
             + 2.0 * D * P + 2.0 * P * K)
+
+
+# ----------------------------------------------------------------------------- Mahalanobis baseline ---
+# The reference's `--score maha` path (utils/detection_util.py:148-207; eval_ood_detection.py:72-79,87-88):
+# class means + one shared precision matrix estimated from ID training features, then per image
+#   score = -max_k ( -0.5 * (f - mu_k)^T P (f - mu_k) )  =  min_k 0.5 * (f - mu_k)^T P (f - mu_k).
+
+def maha_mean_prec(features, batch_labels, n_cls, normalize=False):
+    """``get_mean_prec`` (``utils/detection_util.py:148-180``) given the per-batch feature tensors and label tensors
+    the reference loop sees.  Reproduces it literally, including that ``classwise_idx`` collects the BATCH index
+    ``idx`` once per sample of the batch (``:166-167``) and that those batch indices then index the ROWS of the
+    concatenated feature matrix (``:171-172``)."""
+    from collections import defaultdict
+    classwise_idx = defaultdict(list)
+    all_features = []
+    for idx, (f, labels) in enumerate(zip(features, batch_labels)):
+        f = f.float().clone()
+        if normalize:
+            f /= f.norm(dim=-1, keepdim=True)
+        for label in labels:
+            classwise_idx[int(label)].append(idx)
+        all_features.append(f)
+    all_features = torch.cat(all_features)
+    classwise_mean = torch.empty(n_cls, all_features.shape[1])
+    for cls in range(n_cls):
+        classwise_mean[cls] = torch.mean(all_features[classwise_idx[cls]].float(), dim=0)
+        if normalize:
+            classwise_mean[cls] /= classwise_mean[cls].norm(dim=-1, keepdim=True)
+    cov = torch.cov(all_features.T.double())
+    precision = torch.linalg.inv(cov).float()
+    return classwise_mean, precision
+
+
+def maha_scores_from_features(features, classwise_mean, precision, normalize=False):
+    """One batch of ``get_Mahalanobis_score`` (``:195-205``): features ``[b, P]`` -> ``[b]`` float32."""
+    f = torch.as_tensor(features).float().clone()
+    if normalize:
+        f /= f.norm(dim=-1, keepdim=True)
+    cols = []
+    for i in range(classwise_mean.shape[0]):
+        zero_f = f - classwise_mean[i]
+        cols.append((-0.5 * torch.mm(torch.mm(zero_f, precision), zero_f.t()).diag()).view(-1, 1))
+    score, _ = torch.max(torch.cat(cols, 1), dim=1)
+    return (-score).numpy().astype(np.float32)
+
+
+def maha_scores(images, sd, cfg: VisionCfg, classwise_mean, precision, batch=64, normalize=False, in_dist=True):
+    """``get_Mahalanobis_score`` (``:182-207``) over a stream, including its batch rule: for ``in_dist=False`` the
+    loop stops at batch ``len(dataset) // batch_size`` (``:191-192``), i.e. a trailing partial batch of an OOD set is
+    dropped."""
+    images = torch.as_tensor(images)
+    n = images.shape[0]
+    out = []
+    with torch.no_grad():
+        for bi, s in enumerate(range(0, n, batch)):
+            if bi >= n // batch and in_dist is False:
+                break
+            out.append(maha_scores_from_features(image_features(images[s:s + batch], sd, cfg), classwise_mean, precision, normalize))
+    return np.concatenate(out) if out else np.zeros((0,), np.float32)

@@ -112,3 +112,26 @@ def test_resize_oracle_matches_golden_digests(golden_dir):
     for i, ((h, w), want) in enumerate(zip(z["sizes"], z["sha1"])):
         got = R.resize_center_crop_u8(image(int(h), int(w), i))
         assert hashlib.sha1(got.tobytes()).hexdigest() == str(want), f"{h}x{w}"
+
+
+@pytest.mark.parametrize("tag,normalize", [("u", False), ("n", True)])
+def test_maha_oracle_reproduces_reference(golden_dir, tag, normalize):
+    """Mahalanobis baseline: the oracle restatement against outputs of the UNMODIFIED reference get_mean_prec /
+    get_Mahalanobis_score (utils/detection_util.py:148-207) stored by oracle/make_golden_maha.py -- statistics,
+    scores, and the dropped trailing OOD batch."""
+    from oracle.make_golden_maha import SPEC, build_inputs
+    z = np.load(os.path.join(golden_dir, "maha_tiny.npz"))
+    cfg, sd, train, train_labels, id_imgs, ood = build_inputs()
+    B = SPEC["batch"]
+    with torch.no_grad():
+        feats = [O.image_features(torch.from_numpy(train[s:s + B]), sd, cfg) for s in range(0, len(train), B)]
+    labs = [train_labels[s:s + B] for s in range(0, len(train), B)]
+    mean, prec = O.maha_mean_prec(feats, labs, SPEC["n_cls"], normalize)
+    np.testing.assert_allclose(mean.numpy(), z[f"mean_{tag}"], rtol=1e-4, atol=1e-6)
+    ref_mean, ref_prec = torch.from_numpy(z[f"mean_{tag}"]), torch.from_numpy(z[f"prec_{tag}"])
+    o_in = O.maha_scores(id_imgs, sd, cfg, ref_mean, ref_prec, B, normalize, True)
+    o_out = O.maha_scores(ood, sd, cfg, ref_mean, ref_prec, B, normalize, False)
+    assert o_out.shape == z[f"ref_out_{tag}"].shape == ((len(ood) // B) * B,)
+    scale = float(np.abs(z[f"ref_in_{tag}"]).max())
+    np.testing.assert_allclose(o_in, z[f"ref_in_{tag}"], rtol=0, atol=2e-4 * scale)
+    np.testing.assert_allclose(o_out, z[f"ref_out_{tag}"], rtol=0, atol=2e-4 * scale)
