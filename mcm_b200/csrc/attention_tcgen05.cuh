@@ -35,7 +35,12 @@
 // pipelined TMEM loads (MCM_ATC_PIPE, +13 %), one pass per row with a lazily raised maximum (MCM_ATC_SINGLE_PASS,
 // +6 %), two threads per row, one MMA issuer warp per buffer, forcing the two groups out of phase (all +-5 %), and
 // moving the 69 rows beyond the first 128 of ViT-B/16 to four mma.sync warps so that an item needs ONE unit (2.2 x
-// slower: a 16-row mma.sync tile over 208 keys takes one warp ~8 k cycles, five of them per item on four warps).  96 us per layer call vs 293 us for the
+// slower: a 16-row mma.sync tile over 208 keys takes one warp ~8 k cycles, five of them per item on four warps).
+// Two more, both neutral or worse although each removes what a model of the kernel says is its bound: O in a TMEM tile
+// outside the score buffers so that the next-but-one Q K^T is issued right behind P.V instead of after the O drain
+// (97.7 vs 97.9 us), and keeping 1 / 2 / 3 of the seven 32-key score chunks in registers between the two softmax
+// passes to relieve the 64 B/clk TMEM read port (245 KB per unit = 3.8 k cycles, the measured unit time): 106 / 112 /
+// 123 us against 103 for the same code keeping none.  96 us per layer call vs 293 us for the
 // mma.sync kernel; the next step is a third unit in flight (split the keys, rescale O in TMEM).
 //
 // qkv: fp16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)
