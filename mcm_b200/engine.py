@@ -34,7 +34,7 @@ def _score_kind(score: str) -> int:
         return _lib.SCORE_KINDS[score]
     except KeyError:
         raise ValueError(f"score {score!r} is not part of the B200 path (choices: {sorted(_lib.SCORE_KINDS)}); "
-                         "'maha' is a different method (utils/detection_util.py:148-207)") from None
+                         "'maha' goes through get_Mahalanobis_score / McmEngine.maha_score (utils/detection_util.py:148-207)") from None
 
 
 class McmEngine:
