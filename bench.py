@@ -345,7 +345,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
             "config": {"workload": f"CLIP {args.model} image encoder + MCM scoring, K={K} prompt bank (BASELINE "
-                                   f"configs[2] shape), synthetic 224x224 fp32 stream, random-init weights",
+                                   f"configs[{3 if args.model == 'ViT-L/14' else 2}] shape), synthetic 224x224 fp32 stream, "
+                                   f"random-init weights",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": f"resident input pool {len(pool)} x {B * 3 * 224 * 224 * 4 / 1e6:.0f} MB rotates (> 126 MB L2)",
                        "precision": "fp16 tensor-core operands, fp32 accumulate / residual / LayerNorm / softmax / tail"},
