@@ -137,6 +137,12 @@ int mcm_score_stream_host_u8(McmHandle* h, const uint8_t* images_host, int64_t n
 int mcm_resize_crop_u8(McmHandle* h, const uint8_t* src_dev, const int64_t* offsets_host, const int32_t* hs_host,
                        const int32_t* ws_host, int32_t n, uint8_t* dst_dev, void* stream);
 
+/* The whole loop of utils/detection_util.py:220-249 INCLUDING the preprocess, from decoded images in HOST memory: image i is
+ * uint8 [hs[i], ws[i], 3] at byte offsets[i] of `packed_host` (pinned for full copy bandwidth).  Batches of `batch` images
+ * are copied host->device on a copy stream while the previous batch is resized, cropped, normalised and scored.  Synchronous. */
+int mcm_score_stream_host_images(McmHandle* h, const uint8_t* packed_host, const int64_t* offsets, const int32_t* hs,
+                                 const int32_t* ws, int64_t n, int32_t batch, float T, int32_t score_kind, float* scores_host);
+
 /* The host half of mcm_resize_crop_u8 for ONE h x w image (no device needed): the fixed-point resampling tables of the
  * `size` output columns / rows that survive the crop, `[first source index, count, k[ksize]]` per output, ksize2 =
  * {ksize_h, ksize_v}; table_h / table_v hold `cap` int32 each.  Lets the CPU tests check the planner against Pillow. */

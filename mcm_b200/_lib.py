@@ -53,6 +53,8 @@ SIGNATURES = {
     "mcm_set_maha": (C.c_int, [_H, _P, _P, C.c_int32, C.c_int32]),
     "mcm_maha_score": (C.c_int, [_H, _P, C.c_int32, _P, _P]),
     "mcm_dbg_maha_from_features": (C.c_int, [_H, _P, C.c_int32, _P, _P]),
+    "mcm_score_stream_host_images": (C.c_int, [_H, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
+                                              C.c_int32, C.c_float, C.c_int32, _P]),
     "mcm_launch_count": (C.c_int64, [_H]),
     "mcm_reset_launch_count": (None, [_H]),
     "mcm_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),

@@ -123,6 +123,10 @@ struct McmHandle {
     cudaEvent_t rc_ev[2] = {nullptr, nullptr};
     int rc_slot = 0;
     int rc_smem_attr = 0;
+    // ragged host stream (mcm_score_stream_host_images): raw packed images of one batch (two slots), resized batch
+    uint8_t* raw_buf[2] = {nullptr, nullptr};
+    size_t raw_cap[2] = {0, 0};
+    uint8_t* rz_buf = nullptr;
 
     int64_t launches = 0;
 
@@ -851,6 +855,7 @@ void mcm_destroy(McmHandle* h) {
     fr(h->img_buf[0]); fr(h->img_buf[1]); fr(h->scores_buf);
     fr(h->x_cls); fr(h->t_ln); fr(h->t_feat); fr(h->t_logit);
     fr(h->maha_lt); fr(h->maha_c); fr(h->maha_g);
+    fr(h->raw_buf[0]); fr(h->raw_buf[1]); fr(h->rz_buf);
     for (int i = 0; i < 2; ++i) {
         fr(h->rc_dev[i]);
         if (h->rc_host[i]) cudaFreeHost(h->rc_host[i]);
@@ -1111,6 +1116,71 @@ int mcm_dbg_maha_from_features(McmHandle* h, const float* feats, int32_t b, floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MCM_CUDA(h, cudaMemcpyAsync(h->t_feat, feats, (size_t)b * h->P * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return launch_maha(h, h->t_feat, b, scores, st);
+}
+
+int mcm_score_stream_host_images(McmHandle* h, const uint8_t* packed_host, const int64_t* offsets, const int32_t* hs, const int32_t* ws,
+                                 int64_t n, int32_t batch, float T, int32_t kind, float* scores_host) {
+    int rc = check_ready(h, batch, true);
+    if (rc) return rc;
+    if (n == 0) return MCM_OK;
+    if (n < 0 || batch <= 0) return fail(h, MCM_EINVAL, "n must be >= 0 and batch positive");
+    if (!packed_host || !offsets || !hs || !ws || !scores_host) return fail(h, MCM_EINVAL, "mcm_score_stream_host_images: NULL argument");
+    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t out_elems = (size_t)3 * h->cfg.image_size * h->cfg.image_size;
+    if (!h->s_copy) {
+        MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MCM_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            MCM_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            if ((rc = dev_alloc(h, &h->img_buf[i], (size_t)h->cfg.max_batch * out_elems, false))) return rc;
+        }
+    }
+    if (!h->rz_buf && (rc = dev_alloc(h, &h->rz_buf, (size_t)h->cfg.max_batch * out_elems, false))) return rc;
+    if (n > h->scores_cap) {
+        if (h->scores_buf) cudaFree(h->scores_buf);
+        h->scores_buf = nullptr;
+        h->scores_cap = 0;
+        if ((rc = dev_alloc(h, &h->scores_buf, (size_t)n, false))) return rc;
+        h->scores_cap = n;
+    }
+    std::vector<int64_t> rel(static_cast<size_t>(batch));
+    int64_t done = 0;
+    int it = 0;
+    while (done < n) {
+        const int cur = static_cast<int>(std::min<int64_t>(batch, n - done));
+        const int slot = it & 1;
+        // byte span of this batch in the packed host buffer (images need not be in offset order)
+        int64_t lo = offsets[done], hi = 0;
+        for (int i = 0; i < cur; ++i) {
+            const int64_t o = offsets[done + i], e = o + (int64_t)hs[done + i] * ws[done + i] * 3;
+            if (o < 0 || hs[done + i] <= 0 || ws[done + i] <= 0) return fail(h, MCM_EINVAL, "image %lld: bad offset / size", (long long)(done + i));
+            lo = std::min(lo, o);
+            hi = std::max(hi, e);
+        }
+        for (int i = 0; i < cur; ++i) rel[i] = offsets[done + i] - lo;
+        const size_t span = static_cast<size_t>(hi - lo);
+        if (it >= 2) MCM_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_done[slot], 0));
+        if (span > h->raw_cap[slot]) {      // grow: the slot's previous user has to be done with the old buffer
+            if (it >= 2) MCM_CUDA(h, cudaEventSynchronize(h->ev_done[slot]));
+            if (h->raw_buf[slot]) cudaFree(h->raw_buf[slot]);
+            h->raw_buf[slot] = nullptr;
+            h->raw_cap[slot] = 0;
+            if ((rc = dev_alloc(h, &h->raw_buf[slot], span + span / 4, false))) return rc;
+            h->raw_cap[slot] = span + span / 4;
+        }
+        MCM_CUDA(h, cudaMemcpyAsync(h->raw_buf[slot], packed_host + lo, span, cudaMemcpyHostToDevice, h->s_copy));
+        MCM_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_copy));
+        MCM_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
+        if ((rc = mcm_resize_crop_u8(h, h->raw_buf[slot], rel.data(), hs + done, ws + done, cur, h->rz_buf, h->s_comp))) return rc;
+        if ((rc = score_any(h, h->rz_buf, true, cur, T, kind, h->scores_buf + done, h->s_comp))) return rc;
+        MCM_CUDA(h, cudaEventRecord(h->ev_done[slot], h->s_comp));
+        done += cur;
+        ++it;
+    }
+    MCM_CUDA(h, cudaMemcpyAsync(scores_host, h->scores_buf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->s_comp));
+    MCM_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    return MCM_OK;
 }
 
 int mcm_set_normalization(McmHandle* h, const float* mean3, const float* std3) {

@@ -261,6 +261,29 @@ class McmEngine:
                 ws.ctypes.data_as(C.POINTER(C.c_int32)), n, _ptr(out), self._stream()))
         return out
 
+    def score_stream_host_images(self, packed, offsets, hs, ws, batch: Optional[int] = None, T: float = 1.0,
+                                 score: str = "MCM") -> np.ndarray:
+        """The whole evaluation stream from decoded images packed in one HOST uint8 buffer (image ``i`` is
+        ``[hs[i], ws[i], 3]`` at byte ``offsets[i]``): pipelined H2D, device preprocess, scoring; float32 numpy ``[n]``."""
+        t = torch.as_tensor(packed)
+        if t.device.type != "cpu" or t.dtype != torch.uint8 or t.dim() != 1 or not t.is_contiguous():
+            raise ValueError("packed must be a contiguous 1-D uint8 CPU tensor / ndarray")
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        hs = np.ascontiguousarray(hs, dtype=np.int32)
+        ws = np.ascontiguousarray(ws, dtype=np.int32)
+        n = int(offsets.shape[0])
+        if hs.shape != (n,) or ws.shape != (n,):
+            raise ValueError("offsets, hs and ws must have one entry per image")
+        if n and (offsets.min() < 0 or int((offsets + hs.astype(np.int64) * ws * 3).max()) > t.numel()):
+            raise ValueError("an image lies outside the packed buffer")
+        out = np.empty((n,), dtype=np.float32)
+        if n:
+            self._check(self._lib.mcm_score_stream_host_images(
+                self._h, _ptr(t), offsets.ctypes.data_as(C.POINTER(C.c_int64)), hs.ctypes.data_as(C.POINTER(C.c_int32)),
+                ws.ctypes.data_as(C.POINTER(C.c_int32)), n, int(batch or self.max_batch), float(T), _score_kind(score),
+                C.c_void_p(out.ctypes.data)))
+        return out
+
     def score_images(self, images, T: float = 1.0, score: str = "MCM") -> torch.Tensor:
         """Decoded RGB images of arbitrary sizes -> scores: the WHOLE reference preprocess (Resize, CenterCrop, ToTensor,
         Normalize) and the scoring path on the device.  Returns a device tensor ``[n]``."""

@@ -220,5 +220,16 @@ def test_resize_crop_on_device_matches_oracle(tiny_net):
     ref = eng.score(O.preprocess_u8(want).cuda()).cpu().numpy()
     np.testing.assert_array_equal(scores, ref)
     assert eng.resize_crop_u8([]).shape == (0, 224, 224, 3)
+    # the same through the one-call host stream (pipelined H2D + preprocess + scoring), ragged batches
+    sizes_b = np.array([im.size for im in imgs], dtype=np.int64)
+    offs = np.zeros(len(imgs), dtype=np.int64)
+    offs[1:] = np.cumsum(sizes_b[:-1])
+    packed = torch.from_numpy(np.concatenate([im.reshape(-1) for im in imgs])).pin_memory()
+    hs = [im.shape[0] for im in imgs]
+    ws = [im.shape[1] for im in imgs]
+    for batch in (32, 5):
+        np.testing.assert_array_equal(eng.score_stream_host_images(packed, offs, hs, ws, batch=batch), ref)
+    with pytest.raises(ValueError):
+        eng.score_stream_host_images(packed, offs + 10 ** 9, hs, ws)
     with pytest.raises(ValueError):
         eng.resize_crop_u8([np.zeros((10, 10), np.uint8)])

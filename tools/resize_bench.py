@@ -56,7 +56,15 @@ for _ in range(reps):
     s = eng.score_images(imgs)
 torch.cuda.synchronize()
 t_all = (time.perf_counter() - t0) / reps
-rec = dict(n=len(imgs), source_mb=mb, packed_call_cpu_ms=1e3 * t_call, packed_device_images_per_s=len(imgs) / t_dev,
+# one-call host stream from a pinned packed buffer: pipelined H2D + device preprocess + scoring
+packed_host = torch.from_numpy(np.concatenate([a.reshape(-1) for a in imgs] * 4)).pin_memory()
+offs4 = np.concatenate([offs + k * int(sizes_b.sum()) for k in range(4)])
+hs4, ws4 = np.tile(hs, 4), np.tile(ws, 4)
+eng.score_stream_host_images(packed_host, offs4[:512], hs4[:512], ws4[:512], batch=256)
+t0 = time.perf_counter()
+eng.score_stream_host_images(packed_host, offs4, hs4, ws4, batch=256)
+t_stream = time.perf_counter() - t0
+rec = dict(n=len(imgs), source_mb=mb, host_stream_images_per_s=len(offs4) / t_stream, host_stream_h2d_gbs=4 * mb / 1e3 / t_stream, packed_call_cpu_ms=1e3 * t_call, packed_device_images_per_s=len(imgs) / t_dev,
            packed_device_source_gbs=mb / 1e3 / t_dev, resize_crop_images_per_s=len(imgs) / t_resize, score_images_per_s=len(imgs) / t_all)
 try:
     from PIL import Image
