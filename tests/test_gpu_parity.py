@@ -173,3 +173,32 @@ def test_uint8_ingest_patch_geometries(engine_factory, cfg_name):
     rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
     report("features_u8", dict(cfg=cfg_name, rel_err=rel))
     assert rel <= 3e-2, rel
+
+
+@pytest.mark.parametrize("cfg_name", ["small", "ViT-B/16"])
+def test_features_with_outlier_channels(cfg_name):
+    """Trained CLIP towers carry "massive activations": a few residual channels two orders of magnitude above the
+    rest.  The LayerNorm fold feeds the RAW residual rows (fp16) to the q/k/v and fc1 projections and subtracts the
+    mean in the epilogue, so such rows are the stress case for its cancellation.  Inject the pattern through
+    pre_layrnorm.bias (the offset rides the residual stream through every layer) and hold the usual feature bound."""
+    from mcm_b200 import synth
+    from mcm_b200.engine import McmEngine
+    from oracle import clip_mcm_oracle as O
+    cfg = synth.CFGS[cfg_name]
+    sd = synth.synth_vision_state_dict(cfg, 5)
+    b = sd["vision_model.pre_layrnorm.bias"].clone()
+    b[5], b[77], b[cfg.width - 3] = 40.0, -60.0, 25.0
+    sd["vision_model.pre_layrnorm.bias"] = b
+    eng = McmEngine.from_state_dict(sd, cfg, max_batch=8)
+    try:
+        imgs = torch.from_numpy(synth.synth_images(4, 31))
+        got = eng.image_features(imgs.cuda()).cpu()
+        with torch.no_grad():
+            ref, hidden = O.image_features(imgs, sd, cfg, return_hidden=True)
+        rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+        ratio = float(hidden.abs().max() / hidden.std())
+        report("features_outliers", dict(cfg=cfg_name, rel_err=rel, max_over_std=ratio))
+        assert ratio > 10           # the stream really carries outliers
+        assert rel <= 3e-2, rel
+    finally:
+        eng.close()
