@@ -108,6 +108,7 @@ class McmEngine:
             raise ValueError(f"text bank must be [K, {self.cfg.proj}], got {tuple(t.shape)}")
         self._check(self._lib.mcm_set_text_bank(self._h, _ptr(t), t.shape[0], 1 if already_unit else 0))
         self.K = int(t.shape[0])
+        self.__dict__.pop("_mcm_bank_key", None)      # detection_util's per-label-set cache no longer describes the bank
 
     # -------------------------------------------------------------------- compute --
     def _check_images(self, images: torch.Tensor) -> int:

@@ -16,6 +16,7 @@ def tiny_net(engine_factory):
     from mcm_b200.engine import B200ClipNet
     eng, sd, cfg = engine_factory("tiny", 5, 32)
     bank = synth.synth_unit_bank(12, cfg.proj, 9)
+    eng.set_text_bank(bank)          # tests that call the engine directly must not depend on test order
     return B200ClipNet(eng, text_bank=bank).eval(), cfg, bank
 
 
