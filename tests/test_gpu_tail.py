@@ -10,7 +10,7 @@ SCORES = ["MCM", "max-logit", "energy", "entropy", "var"]
 
 
 @pytest.mark.parametrize("cfg_name,K,b,T", [("tiny", 10, 7, 1.0), ("small", 100, 9, 2.0), ("ViT-B/16", 1000, 5, 1.0),
-                                            ("ViT-B/16", 1, 4, 1.0)])
+                                            ("ViT-B/16", 1, 4, 1.0), ("tiny", 1001, 3, 0.01), ("tiny", 33, 2, 100.0)])
 def test_tail_matches_oracle(engine_factory, cfg_name, K, b, T):
     from mcm_b200 import synth
     from oracle import clip_mcm_oracle as O
