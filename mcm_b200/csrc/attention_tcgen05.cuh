@@ -27,6 +27,7 @@
 // TMEM map of buffer g (base = g * 256 columns):  S fp32 [0, keys_pad)  ->  P fp16 [0, keys_pad/2)
 //                                                 O fp32 [128, 192)  (dead S columns by the time PV runs)
 // Padded keys (>= S) are masked to probability 0; padded query rows are computed and never stored.
+// Sequences of at most 64 tokens (ViT-B/32: 50) would fill 39 % of a 128-row unit: there a unit carries TWO items (pair_mode).
 //
 // Measured (clock64 phase trace of one CTA, ViT-B/16 shape, tools/attn_sweep.py with the -DMCM_ATC_TRACE
 // build): one unit takes ~7.7 k cycles end to end -- row max 1.4 k, exp2 pass 3.1 k (the warp's own
@@ -67,6 +68,8 @@ constexpr int kAtcXBytes = 3 * 1024;           // per K/V stage: q | k | v of to
 struct AtcParams {
     int b, S, H, keys_pad;   // keys_pad: min(S, 256) rounded up to 16
     int n_extra;             // S - 256 if S > 256 (0 or 1): keys handled outside the tensor core
+    int pair_mode;           // S <= 64 (ViT-B/32): TWO (image, head) items share a unit -- rows / keys 0..63 item 2w, 64..127
+                             // item 2w + 1, keys_pad = 128, a row's probabilities of the other item's keys are zero
     int units_per_item;      // ceil(min(S, 256) / 128)
     float scale_log2e;       // dh^-0.5 * log2(e)
     op16_t* out;
@@ -86,6 +89,9 @@ struct AtcParams {
 constexpr int kAtcMaxS = 257;   // 256 tensor-core keys + 1 extra key
 // keys the tensor core sees, rounded up to the UMMA N granularity
 __host__ __device__ inline int atc_keys_pad(int S) { return ((S < 256 ? S : 256) + 15) / 16 * 16; }
+
+// rows of the K / V TMA box: 64 in pair mode (S <= 64, two boxes make a 128-row tile), else keys_pad
+__host__ __device__ inline int atc_kv_box_rows(int S) { return S <= 64 ? 64 : atc_keys_pad(S); }
 
 __host__ __device__ inline int atc_smem_bytes(int keys_pad) {
     return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + 2 * kAtcXBytes + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
@@ -234,6 +240,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_items = p.b * p.H;
+    const bool pair = p.pair_mode != 0;
+    const int n_work = pair ? (n_items + 1) / 2 : n_items;      // work items of the persistent loops: items, or pairs of items
     const int upi = p.units_per_item;
     const int D = p.H * 64;
 
@@ -263,13 +271,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (elect_one()) {
             // ===== TMA producer =====
             uint32_t ic = 0, uc = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+            for (int item = blockIdx.x; item < n_work; item += gridDim.x, ++ic) {
+                const int kvs = ic & 1;
+                uint8_t* sk = s_kv + kvs * 2 * kv_bytes;
+                if (pair) {
+                    // pair mode: 64-row boxes (tmap_kv) of item 2w and item 2w + 1 (the last item again if n_items is odd)
+                    // stacked into 128-row Q / K / V tiles; 8 KB per box keeps the 128-byte swizzle phase of the rows
+                    mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes);
+                    const int qs = uc % kAtcQStages;
+                    mbar_wait(&q_empty[qs], ((uc / kAtcQStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[qs], kAtcQBytes);
+                    for (int half = 0; half < 2; ++half) {
+                        const int it2 = min(2 * item + half, n_items - 1);
+                        const int img2 = it2 / p.H, h2 = it2 - img2 * p.H;
+                        tma_load_2d(sk + half * 8192, &tmap_kv, &kv_full[kvs], D + h2 * 64, img2 * p.S);
+                        tma_load_2d(sk + kv_bytes + half * 8192, &tmap_kv, &kv_full[kvs], 2 * D + h2 * 64, img2 * p.S);
+                        tma_load_2d(s_q + qs * kAtcQBytes + half * 8192, &tmap_kv, &q_full[qs], h2 * 64, img2 * p.S);
+                    }
+                    ++uc;
+                    continue;
+                }
                 const int img = item / p.H, h = item - img * p.H;
                 const int row0 = img * p.S;
-                const int kvs = ic & 1;
                 mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes + (p.n_extra > 0 ? kAtcXBytes : 0));
-                uint8_t* sk = s_kv + kvs * 2 * kv_bytes;
                 tma_load_2d(sk, &tmap_kv, &kv_full[kvs], D + h * 64, row0);
                 tma_load_2d(sk + kv_bytes, &tmap_kv, &kv_full[kvs], 2 * D + h * 64, row0);
                 if (p.n_extra > 0) {
@@ -289,7 +315,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     } else if (warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer =====
-            const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+            const int my_items = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
             const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
             const uint32_t idesc_qk = make_idesc_f16(128, static_cast<uint32_t>(p.keys_pad));
             const uint32_t idesc_pv = make_idesc_f16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
@@ -468,10 +494,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
         const uint32_t t_s = tmem_base + t_lane + g * 256;
         const uint32_t stg = smem_u32(s_stage + (warp - 2) * 32 * 128);   // shared-space address of this warp's staging tile
-        const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+        const int my_items = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
         const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
-        const int nfull = p.keys_pad >> 5;
-        const bool rem16 = (p.keys_pad & 16) != 0;
+        // pair mode: this warp's rows belong to item `half` of the pair and see only that item's 64 key columns
+        const int half = pair ? (quad >> 1) : 0;
+        const uint32_t t_sr = t_s + (pair ? half * 64 : 0);     // first score column of this warp's keys
+        const uint32_t t_pw = t_s + (pair ? half * 32 : 0);     // first (packed fp16) probability column of those keys
+        const int nfull = pair ? 2 : p.keys_pad >> 5;
+        const bool rem16 = !pair && (p.keys_pad & 16) != 0;
         const float c = p.scale_log2e;
         const int S_tc = p.S - p.n_extra;    // keys that go through the tensor core
         // Stagger the two groups by half a period: group 1 starts its first softmax only when group 0 has
@@ -484,10 +514,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const uint32_t j = u >> 1;
             const uint32_t iu = u / upi;
             const int mt = static_cast<int>(u - iu * upi);
-            const int item = static_cast<int>(blockIdx.x) + static_cast<int>(iu) * static_cast<int>(gridDim.x);
+            const int work = static_cast<int>(blockIdx.x) + static_cast<int>(iu) * static_cast<int>(gridDim.x);
+            const int item = pair ? 2 * work + half : work;
             const int img = item / p.H, h = item - img * p.H;
-            const int wrow0 = mt * 128 + quad * 32;       // first query row (within the image) of this warp
-            const bool warp_valid = wrow0 < p.S;
+            const int wrow0 = pair ? (quad & 1) * 32 : mt * 128 + quad * 32;       // first query row (within the image) of this warp
+            const bool warp_valid = item < n_items && wrow0 < p.S;
             // the extra key (ViT-L/14's 257th token): this row's raw score against it, on the CUDA cores,
             // while the tensor core is still busy with Q K^T of the other 256
             float s_x = 0.f;
@@ -512,7 +543,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 float sum0 = 0.f, sum1 = 0.f;
                 for (int ch = 0; ch < nfull; ++ch) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                    tmem_ld_32x32b_x32(t_sr + ch * 32, v);
                     tmem_ld_wait();
                     float cm = atc_chunk_max(v, ch * 32, S_tc, -INFINITY);
                     if (ch == 0 && p.n_extra > 0) cm = fmaxf(cm, s_x);
@@ -520,16 +551,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     const bool raise = cm > m + 8.0f;
                     if (__any_sync(0xffffffffu, raise)) {
                         const float f = raise ? ex2_approx(m - cm) : 1.0f;     // m = -inf (first chunk): f = 0, nothing to scale
-                        if (ch > 0) atc_rescale_p(t_s, ch, f);
+                        if (ch > 0) atc_rescale_p(t_pw, ch, f);
                         sum0 *= f;
                         sum1 *= f;
                         if (raise) m = cm;
                     }
-                    atc_chunk_exp(v, ch * 32, S_tc, c, m, sum0, sum1, t_s + ch * 16);
+                    atc_chunk_exp(v, ch * 32, S_tc, c, m, sum0, sum1, t_pw + ch * 16);
                 }
                 if (rem16) {
                     uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
+                    tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
                     tmem_ld_wait();
                     float cm = -INFINITY;
 #pragma unroll
@@ -540,7 +571,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     const bool raise = cm > m + 8.0f;
                     if (__any_sync(0xffffffffu, raise)) {
                         const float f = raise ? ex2_approx(m - cm) : 1.0f;
-                        if (nfull > 0) atc_rescale_p(t_s, nfull, f);
+                        if (nfull > 0) atc_rescale_p(t_pw, nfull, f);
                         sum0 *= f;
                         sum1 *= f;
                         if (raise) m = cm;
@@ -555,7 +586,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         sum1 += p1;
                         pk[e] = pack_op16x2(p0, p1);
                     }
-                    tmem_st_32x32b_x8(t_s + nfull * 16, pk);
+                    tmem_st_32x32b_x8(t_pw + nfull * 16, pk);
                 }
                 tmem_st_wait();
                 row_sum = sum0 + sum1;
@@ -573,15 +604,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 for (int ch = 0; ch < nfull; ch += 2) {
                     uint32_t va[32], vb[32];
                     const bool two = ch + 1 < nfull;
-                    tmem_ld_32x32b_x32(t_s + ch * 32, va);
-                    if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
+                    tmem_ld_32x32b_x32(t_sr + ch * 32, va);
+                    if (two) tmem_ld_32x32b_x32(t_sr + ch * 32 + 32, vb);
                     tmem_ld_wait();
                     mx = atc_chunk_max(va, ch * 32, S_tc, mx);
                     if (two) mx = atc_chunk_max(vb, ch * 32 + 32, S_tc, mx);
                 }
                 if (rem16) {
                     uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
+                    tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
@@ -596,30 +627,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 #if MCM_ATC_PIPE
                 {
                     uint32_t va[32], vb[32];
-                    if (nfull > 0) tmem_ld_32x32b_x32(t_s, va);
+                    if (nfull > 0) tmem_ld_32x32b_x32(t_sr, va);
                     for (int ch = 0; ch < nfull; ch += 2) {
                         tmem_ld_wait();
                         const bool two = ch + 1 < nfull;
-                        if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
-                        atc_chunk_exp(va, ch * 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16);
+                        if (two) tmem_ld_32x32b_x32(t_sr + ch * 32 + 32, vb);
+                        atc_chunk_exp(va, ch * 32, S_tc, c, mc, sum0, sum1, t_pw + ch * 16);
                         if (two) {
                             tmem_ld_wait();
-                            if (ch + 2 < nfull) tmem_ld_32x32b_x32(t_s + ch * 32 + 64, va);
-                            atc_chunk_exp(vb, ch * 32 + 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16 + 16);
+                            if (ch + 2 < nfull) tmem_ld_32x32b_x32(t_sr + ch * 32 + 64, va);
+                            atc_chunk_exp(vb, ch * 32 + 32, S_tc, c, mc, sum0, sum1, t_pw + ch * 16 + 16);
                         }
                     }
                 }
 #else
                 for (int ch = 0; ch < nfull; ++ch) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_s + ch * 32, v);
+                    tmem_ld_32x32b_x32(t_sr + ch * 32, v);
                     tmem_ld_wait();
-                    atc_chunk_exp(v, ch * 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16);
+                    atc_chunk_exp(v, ch * 32, S_tc, c, mc, sum0, sum1, t_pw + ch * 16);
                 }
 #endif
                 if (rem16) {
                     uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
+                    tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
                     tmem_ld_wait();
                     uint32_t pk[8];
 #pragma unroll
@@ -631,7 +662,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         sum1 += p1;
                         pk[e] = pack_op16x2(p0, p1);
                     }
-                    tmem_st_32x32b_x8(t_s + nfull * 16, pk);
+                    tmem_st_32x32b_x8(t_pw + nfull * 16, pk);
+                }
+                if (pair) {     // probability 0 for the 64 keys of the other item (for half 0 these columns held this row's
+                                // own scores 32..63: consumed by now)
+                    uint32_t zero[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) zero[e] = 0u;
+                    tmem_st_32x32b_x16(t_s + (1 - half) * 32, zero);
+                    tmem_st_32x32b_x16(t_s + (1 - half) * 32 + 16, zero);
                 }
                 tmem_st_wait();
                 row_sum = sum0 + sum1;

@@ -453,7 +453,8 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     p.b = b;
     p.S = S;
     p.H = H;
-    p.keys_pad = atc_keys_pad(S);
+    p.pair_mode = S <= 64 ? 1 : 0;             // two (image, head) items per 128-row unit (ViT-B/32)
+    p.keys_pad = p.pair_mode ? 128 : atc_keys_pad(S);
     p.n_extra = S > 256 ? S - 256 : 0;
     p.units_per_item = ((S < 256 ? S : 256) + 127) / 128;   // query rows >= 256 go to the tail-row warp
     p.scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
@@ -471,7 +472,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
         MCM_CUDA(h, cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    const int items = b * H;
+    const int items = p.pair_mode ? (b * H + 1) / 2 : b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
     MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
@@ -830,7 +831,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         h->attn_mma = e && e[0] == '1';
         if (h->S <= kAtcMaxS) {
             MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
-            MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, atc_keys_pad(h->S)));
+            MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, atc_kv_box_rows(h->S)));
             MCM_TRY(make_tmap(h, &h->tm_qkv_x, h->qkv, h->m_pad, 3 * D, 8));
         }
     }
@@ -1364,7 +1365,7 @@ int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t
     if (S <= kAtcMaxS && !h->attn_mma) {
         int rc;
         if ((rc = make_tmap(h, &tq, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 128))) return rc;
-        if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, atc_keys_pad(S)))) return rc;
+        if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, atc_kv_box_rows(S)))) return rc;
         if ((rc = make_tmap(h, &tx, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 8))) return rc;
     }
     return launch_attention(h, tq, tkv, tx, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,

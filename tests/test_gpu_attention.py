@@ -7,9 +7,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("b,S,H", [(1, 50, 2), (3, 197, 4), (2, 197, 12), (2, 257, 16), (1, 16, 1), (1, 17, 1),
-                                   (1, 255, 2), (2, 256, 3), (3, 257, 2), (37, 257, 16), (1, 258, 2), (1, 290, 1)])
+                                   (1, 255, 2), (2, 256, 3), (3, 257, 2), (37, 257, 16), (1, 258, 2), (1, 290, 1),
+                                   (3, 50, 5), (2, 64, 3), (5, 33, 1), (7, 50, 12), (1, 65, 2)])
 def test_attention(engine_factory, b, S, H):
-    """S <= 256: tensor-core keys only; S = 257 (ViT-L/14): 256 tensor-core keys + the extra key on the CUDA
+    """S <= 64 (ViT-B/32): two (image, head) items per 128-row unit, odd item counts included; S <= 256: tensor-core keys only; S = 257 (ViT-L/14): 256 tensor-core keys + the extra key on the CUDA
     cores; S > 257 falls back to the warp-level mma.sync kernel."""
     eng, _, _ = engine_factory("tiny", 5, 8)
     g = torch.Generator(device="cuda").manual_seed(S * 13 + H)
