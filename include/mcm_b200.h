@@ -17,9 +17,13 @@
  *   - every function returns 0 on success, a non-zero MCM_E* code on failure; the text of the last
  *     failure is available from mcm_last_error(handle) (or mcm_last_error(NULL) for mcm_create).
  *   - a handle is bound to one CUDA device and is NOT thread-safe (the reference drives one device
- *     from one Python thread, eval_ood_detection.py:57-58).
+ *     from one Python thread, eval_ood_detection.py:57-58).  Every entry point selects the handle's
+ *     device for its own duration and restores the caller's current device before it returns.
  *   - device work is enqueued on the caller's stream and is asynchronous; the caller synchronises
  *     when it reads the scores.  Nothing is allocated inside mcm_score / mcm_image_features.
+ *   - one handle owns ONE activation workspace: consecutive forwards on the same handle are ordered
+ *     against each other on the device (event wait), whatever streams they are enqueued on -- also
+ *     the mcm_score_stream_host* calls, which run on the handle's own streams.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef MCM_B200_H_
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MCM_ABI_VERSION 1
+#define MCM_ABI_VERSION 2
 
 enum {
     MCM_OK = 0,
@@ -169,8 +173,33 @@ void mcm_reset_launch_count(McmHandle* h);
  * out_proj, layer_norm2 and the MLP only for the CLS query row of every image -- the only row the
  * reference consumes afterwards (pooled = last_hidden_state[:, 0], HF:685).  Results are
  * identical; 0 runs the full last layer (the number bench.py reports beside the default). */
-enum { MCM_OPT_CLS_SHORTCUT = 1 };
+enum {
+    MCM_OPT_CLS_SHORTCUT = 1,
+    /* MCM_OPT_PRECISION: arithmetic of the tensor-core operands.
+     *   MCM_PRECISION_FP16 (0, default): one fp16 value per operand element (fp32 accumulation, residual stream,
+     *     LayerNorm statistics, softmax and tail).  Scores within ~1e-7 of the fp32 reference, AUROC within 0.01 pt;
+     *     FPR95 -- a COUNT of images above a threshold -- can move by a few images per 10 000.
+     *   MCM_PRECISION_SPLIT (1): every operand element is an fp16 (hi, lo) pair (~22 significant bits) and every
+     *     product the three-term sum A_hi W_hi + A_lo W_hi + A_hi W_lo: fp32-class results at 3x the tensor work.
+     *     This is the mode in which AUROC / FPR95 agree with the reference (fp32 end to end,
+     *     utils/detection_util.py:225-236) to the 0.05 pt of the parity bar on every stream.
+     *   The first switch to MCM_PRECISION_SPLIT allocates the low-half activation buffers (synchronises). */
+    MCM_OPT_PRECISION = 2,
+    /* MCM_OPT_CUDA_GRAPH (default 0): mcm_score / mcm_image_features (and their _u8 / stream_host forms) replay a
+     * CUDA graph captured per (entry point, batch size, option set) instead of ~70 individual launches:
+     * for small batches, where the forward is launch-bound. */
+    MCM_OPT_CUDA_GRAPH = 3
+};
+enum { MCM_PRECISION_FP16 = 0, MCM_PRECISION_SPLIT = 1 };
 int mcm_set_option(McmHandle* h, int32_t option, int32_t value);
+
+/* Collation of the per-rank scores of a sharded stream: every rank contributes `n_local_padded`
+ * fp32 scores (the tail rank pads, mirroring the reference's own `[:len(loader.dataset)]` trim,
+ * utils/detection_util.py:249), all ranks receive the concatenation in rank order.  `nccl_comm` is the caller's
+ * `ncclComm_t` (passed as void*; the library resolves ncclAllGather from the NCCL already loaded in the process --
+ * torch's -- or from libnccl.so.2, and fails with MCM_EUNSUPPORTED if there is none).  Asynchronous on `stream`. */
+int mcm_allgather_scores(McmHandle* h, void* nccl_comm, const float* local_dev, int32_t n_local_padded, float* all_dev,
+                         void* stream);
 
 /* Optional per-launch timing for bench.py's roofline: while enabled, every kernel launch of a
  * forward is bracketed by CUDA events on the launching stream.  mcm_profile_read synchronises the
@@ -198,6 +227,10 @@ int32_t mcm_abi_version(void);
  * epi 2: out f32  = resid + acc + bias    (resid may alias out) */
 int mcm_dbg_gemm(McmHandle* h, const void* a_f16, const void* w_f16, const float* bias, const float* resid,
                  void* out, int32_t M, int32_t N, int32_t K, int32_t epi, void* stream);
+/* The split-precision GEMM on given operand pairs (a = a_hi + a_lo, w = w_hi + w_lo, all fp16 row-major):
+ * out f32 = resid + (a_hi w_hi^T + a_lo w_hi^T + a_hi w_lo^T) + bias  (resid may alias out). */
+int mcm_dbg_gemm_split(McmHandle* h, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                       const float* bias, const float* resid, float* out, int32_t M, int32_t N, int32_t K, void* stream);
 /* The LayerNorm-folded projections the forward actually runs (csrc/gemm_tcgen05.cuh): layer_norm1 / layer_norm2
  * (HF:371,380) never materialise; the projection reads the RAW fp16 residual rows and its epilogue applies the row
  * statistics.
@@ -222,6 +255,9 @@ int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* gamma, const fl
 /* softmax(q k^T / 8) v per (image, head) (HF:261-279,318-331): qkv fp16 [b*S, 3*H*64] -> o fp16 [b*S, H*64]. */
 int mcm_dbg_attention(McmHandle* h, const void* qkv_f16, void* o_f16, int32_t b, int32_t S, int32_t H,
                       void* stream);
+/* The same in the split-precision mode: qkv = qkv_hi + qkv_lo, o = o_hi + o_lo. */
+int mcm_dbg_attention_split(McmHandle* h, const void* qkv_hi, const void* qkv_lo, void* o_hi, void* o_lo, int32_t b,
+                            int32_t S, int32_t H, void* stream);
 /* CLS pool + post_layernorm + visual_projection (HF:685-686,860-861) + the scoring tail.
  * x f32 [b*S, D] (row b*S is the CLS token); feats (may be NULL) [b,P]; scores (may be NULL) [b]. */
 int mcm_dbg_tail(McmHandle* h, const float* x, int32_t b, float T, int32_t score_kind, float* feats, float* scores,

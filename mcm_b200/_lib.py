@@ -10,7 +10,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = range(6)
 
@@ -18,6 +18,11 @@ PROF_KINDS = ["patchify", "gemm_patch", "embed_finish", "gemm_qkv", "attention",
               "gemm_fc1", "gemm_fc2", "tail", "gemm_other"]
 
 OPT_CLS_SHORTCUT = 1
+OPT_PRECISION = 2
+OPT_CUDA_GRAPH = 3
+PRECISION_FP16 = 0
+PRECISION_SPLIT = 1
+PRECISIONS = {"fp16": PRECISION_FP16, "split": PRECISION_SPLIT, 0: PRECISION_FP16, 1: PRECISION_SPLIT}
 
 SCORE_KINDS = {"MCM": 0, "max-logit": 1, "energy": 2, "entropy": 3, "var": 4}
 
@@ -58,6 +63,9 @@ SIGNATURES = {
     "mcm_launch_count": (C.c_int64, [_H]),
     "mcm_reset_launch_count": (None, [_H]),
     "mcm_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "mcm_allgather_scores": (C.c_int, [_H, _P, _P, C.c_int32, _P, _P]),
+    "mcm_dbg_gemm_split": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "mcm_dbg_attention_split": (C.c_int, [_H, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mcm_profile_enable": (C.c_int, [_H, C.c_int32]),
     "mcm_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "mcm_flops_per_image": (C.c_double, [C.POINTER(McmConfig), C.c_int32]),
@@ -74,11 +82,20 @@ SIGNATURES = {
 }
 
 _lib = None
+_lib_override = None
+
+
+def use_library(path: str) -> None:
+    """Development tools only (``tools/``): load an A/B variant built by ``build.build_variant`` instead of the
+    in-tree library.  Must be called before the first engine is created; nothing in the product reads the environment."""
+    global _lib_override
+    if _lib is not None:
+        raise RuntimeError("the mcm_b200 library is already loaded")
+    _lib_override = str(path)
 
 
 def lib_path() -> str:
-    """In-tree library; ``MCM_B200_LIB`` selects an A/B variant built by ``build.build_variant``."""
-    return os.environ.get("MCM_B200_LIB") or _build.LIB_PATH
+    return _lib_override or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(OUT_DIR, "libmcm_b200.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-ldl",
 ]
 
 
@@ -38,7 +38,7 @@ def is_stale() -> bool:
 
 def build_variant(name: str, defines) -> str:
     """A/B builds for GPU experiments: ``_C/libmcm_b200_<name>.so`` compiled with extra ``-D`` flags;
-    select it at run time with ``MCM_B200_LIB=<path>``."""
+    tools select it with ``mcm_b200._lib.use_library(path)`` before the first engine is created."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(OUT_DIR, exist_ok=True)
     out = os.path.join(OUT_DIR, f"libmcm_b200_{name}.so")

@@ -14,7 +14,8 @@
 // Persistent CTAs (one per SM) walk over (image, head) items; every item is cut into 128-query-row
 // units.  Warp roles:
 //   warp 0      TMA producer: K and V of the item ([keys_pad x 64] fp16 boxes, 128-byte swizzle, 2-stage
-//               ring) and the Q tile of every unit (3-stage ring), straight out of the fused QKV buffer.
+//               ring; 3-D tensor map over [image][token][3 D], so key rows beyond the image's S tokens are zero-filled)
+//               and the Q tile of every unit (3-stage ring), straight out of the fused QKV buffer.
 //   warp 1      MMA issuer (one elected thread):  S = Q K^T   as UMMA 128 x keys_pad x 16 (x4, SS mode),
 //                                                 O = P V     as UMMA 128 x 64 x 16 (x keys_pad/16, TS mode:
 //               P is read from TENSOR MEMORY, V from shared memory as an MN-major operand).
@@ -285,9 +286,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     for (int half = 0; half < 2; ++half) {
                         const int it2 = min(2 * item + half, n_items - 1);
                         const int img2 = it2 / p.H, h2 = it2 - img2 * p.H;
-                        tma_load_2d(sk + half * 8192, &tmap_kv, &kv_full[kvs], D + h2 * 64, img2 * p.S);
-                        tma_load_2d(sk + kv_bytes + half * 8192, &tmap_kv, &kv_full[kvs], 2 * D + h2 * 64, img2 * p.S);
-                        tma_load_2d(s_q + qs * kAtcQBytes + half * 8192, &tmap_kv, &q_full[qs], h2 * 64, img2 * p.S);
+                        tma_load_3d(sk + half * 8192, &tmap_kv, &kv_full[kvs], D + h2 * 64, 0, img2);
+                        tma_load_3d(sk + kv_bytes + half * 8192, &tmap_kv, &kv_full[kvs], 2 * D + h2 * 64, 0, img2);
+                        tma_load_3d(s_q + qs * kAtcQBytes + half * 8192, &tmap_kv, &q_full[qs], h2 * 64, 0, img2);
                     }
                     ++uc;
                     continue;
@@ -296,8 +297,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const int row0 = img * p.S;
                 mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes + (p.n_extra > 0 ? kAtcXBytes : 0));
-                tma_load_2d(sk, &tmap_kv, &kv_full[kvs], D + h * 64, row0);
-                tma_load_2d(sk + kv_bytes, &tmap_kv, &kv_full[kvs], 2 * D + h * 64, row0);
+                // tmap_kv is 3-D ([image][token][3 D]): the padded key rows S .. keys_pad - 1 lie outside the image's plane and
+                // arrive as ZEROS -- never another image's (or a stale batch's) rows, whose Inf / NaN would leak through 0 * V
+                tma_load_3d(sk, &tmap_kv, &kv_full[kvs], D + h * 64, 0, img);
+                tma_load_3d(sk + kv_bytes, &tmap_kv, &kv_full[kvs], 2 * D + h * 64, 0, img);
                 if (p.n_extra > 0) {
                     uint8_t* sx = s_xbox + kvs * kAtcXBytes;
 #pragma unroll

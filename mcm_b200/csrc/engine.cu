@@ -20,8 +20,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include "../../include/mcm_b200.h"
 #include "attention_cls.cuh"
@@ -57,11 +61,14 @@ EncodeTiledFn get_encode_fn() {
 
 struct LayerWeights {
     op16_t *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;   // wqkv / w1 hold gamma o W (LayerNorm fold)
+    op16_t *wqkv_lo = nullptr, *wo_lo = nullptr, *w1_lo = nullptr, *w2_lo = nullptr;   // low halves (split-precision mode)
     float *wqkv32 = nullptr, *w132 = nullptr;   // fp32 masters of the two folded weights (refolded by every finalize)
     float *cqkv = nullptr, *dqkv = nullptr, *c1 = nullptr, *d1 = nullptr;   // fold vectors c, d (gemm_tcgen05.cuh)
+    float *cqkv_s = nullptr, *c1_s = nullptr;   // c of the split-precision operands (row sums of hi + lo)
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
     CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+    CUtensorMap tm_wqkv_lo, tm_wo_lo, tm_w1_lo, tm_w2_lo;
 };
 
 }  // namespace
@@ -75,10 +82,11 @@ struct McmHandle {
 
     // weights
     op16_t* wpatch = nullptr;  // [D, Kp]
+    op16_t* wpatch_lo = nullptr;
     float *cls = nullptr, *pos = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr;
     float* wproj = nullptr;  // [P, D]
     std::vector<LayerWeights> layers;
-    CUtensorMap tm_wpatch;
+    CUtensorMap tm_wpatch, tm_wpatch_lo;
     std::vector<uint8_t> loaded;  // one flag per expected tensor
     std::vector<std::string> expected;
     bool finalized = false;
@@ -102,6 +110,10 @@ struct McmHandle {
     float* x_cls = nullptr;                                   // [pad128(max_batch), D] CLS rows of the last layer
     float *t_ln = nullptr, *t_feat = nullptr, *t_logit = nullptr;   // tail scratch: [max_batch, D | P | K]
     CUtensorMap tm_patches, tm_xh, tm_attn, tm_hid;
+    // split-precision mode (MCM_OPT_PRECISION = 1): low halves of every fp16 activation buffer, allocated on first use
+    int precision = MCM_PRECISION_FP16;
+    op16_t *patches_lo = nullptr, *xh_lo = nullptr, *qkv_lo = nullptr, *attn_lo = nullptr, *hid_lo = nullptr;
+    CUtensorMap tm_patches_lo, tm_xh_lo, tm_attn_lo, tm_hid_lo;
     CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
     bool cls_shortcut = true;
@@ -130,6 +142,28 @@ struct McmHandle {
 
     int64_t launches = 0;
 
+    // one workspace per handle: consecutive forwards are ordered by this event, whatever streams they run on
+    cudaEvent_t ev_busy = nullptr;
+    bool busy_recorded = false;
+    cudaStream_t busy_stream = nullptr;
+
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per handle (= per device), not per process
+    std::vector<std::pair<const void*, int>> smem_attr;
+    // epilogue tensor maps (TMA stores / residual loads) by (base, rows, cols, fp32, box columns): encoded once
+    std::map<std::tuple<const void*, uint64_t, uint64_t, int, uint32_t>, CUtensorMap> epi_maps;
+
+    // MCM_OPT_CUDA_GRAPH: graphs of the forward by (images pointer, entry kind, batch, T, score kind, option set)
+    bool use_graph = false;
+    struct GraphKey {
+        const void* images; int u8, b, mode, kind, precision, cls, K; uint32_t t_bits;
+        bool operator<(const GraphKey& o) const {
+            return std::tie(images, u8, b, mode, kind, precision, cls, K, t_bits) <
+                   std::tie(o.images, o.u8, o.b, o.mode, o.kind, o.precision, o.cls, o.K, o.t_bits);
+        }
+    };
+    std::map<GraphKey, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (executable graph, kernels in it)
+    float* t_scores = nullptr;    // [max_batch] scores of a graph replay (copied to the caller's buffer behind it)
+
     // optional per-launch timing (mcm_profile_*): events bracket every launch of a forward
     bool prof_on = false;
     struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -149,6 +183,34 @@ int fail(McmHandle* h, int code, const char* fmt, ...) {
     va_end(ap);
     if (h) h->err = buf; else g_create_error = buf;
     return code;
+}
+
+// Selects the handle's device for the duration of an entry point and restores the caller's current device.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// opt in to `bytes` of dynamic shared memory for `fn` on this handle's device (once per size increase)
+cudaError_t ensure_smem(McmHandle* h, const void* fn, int bytes) {
+    for (auto& e : h->smem_attr)
+        if (e.first == fn) {
+            if (e.second >= bytes) return cudaSuccess;
+            cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (r == cudaSuccess) e.second = bytes;
+            return r;
+        }
+    cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (r == cudaSuccess) h->smem_attr.emplace_back(fn, bytes);
+    return r;
 }
 
 cudaEvent_t prof_event(McmHandle* h) {
@@ -193,6 +255,12 @@ struct ProfScope {
 // Row-major [rows, cols] output (or in-place residual) of a GEMM epilogue: 32-row x box_cols boxes whose smem image
 // is the epilogue's staging tile (inner dimension 64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B).
 int make_tmap_epi(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, bool f32, uint32_t box_cols) {
+    const auto key = std::make_tuple(base, rows, cols, f32 ? 1 : 0, box_cols);
+    auto it = h->epi_maps.find(key);
+    if (it != h->epi_maps.end()) {
+        *m = it->second;
+        return MCM_OK;
+    }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     const uint32_t esz = f32 ? 4 : sizeof(op16_t);
@@ -213,6 +281,8 @@ int make_tmap_epi(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows,
     if (r != CUDA_SUCCESS)
         return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled (epilogue) failed (%d) rows=%llu cols=%llu", (int)r,
                     (unsigned long long)rows, (unsigned long long)cols);
+    if (h->epi_maps.size() > 4096) h->epi_maps.clear();     // callers that keep changing buffers (tests): bounded
+    h->epi_maps.emplace(key, *m);
     return MCM_OK;
 }
 
@@ -237,6 +307,28 @@ int make_tmap(McmHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uin
     return MCM_OK;
 }
 
+// K / V boxes of the attention kernel: the fused QKV buffer [images * S, 3 D] viewed as [images][S][3 D] with boxes of
+// 64 columns x box_rows tokens of ONE image; tokens >= S are out of bounds and zero-filled.
+int make_tmap_kv(McmHandle* h, CUtensorMap* m, const void* base, uint64_t images, uint64_t S, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t gdim[3] = {cols, S, images};
+    cuuint64_t gstr[2] = {cols * sizeof(op16_t), S * cols * sizeof(op16_t)};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+#ifdef MCM_OP_BF16
+    constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+    constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
+    CUresult r = enc(m, kOpType, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, MCM_ECUDA, "cuTensorMapEncodeTiled (K/V) failed (%d) images=%llu S=%llu cols=%llu box_rows=%u", (int)r,
+                    (unsigned long long)images, (unsigned long long)S, (unsigned long long)cols, box_rows);
+    return MCM_OK;
+}
+
 // Launch with programmatic dependent launch (every kernel of the forward chain calls pdl_wait()) and an
 // optional thread-block cluster.
 template <typename... KArgs, typename... Args>
@@ -248,7 +340,11 @@ cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int n = 0;
-    static const bool no_pdl = [] { const char* e = getenv("MCM_PDL"); return !(e && e[0] == '1'); }();   // opt-in: measured 2.5 % slower
+#ifdef MCM_DEBUG
+    static const bool no_pdl = [] { const char* e = getenv("MCM_PDL"); return !(e && e[0] == '1'); }();   // A/B switch: measured 2-4 % slower
+#else
+    constexpr bool no_pdl = true;
+#endif
     if (!no_pdl) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
@@ -272,18 +368,15 @@ inline int cuda_rc(McmHandle* h, cudaError_t e) {
 
 inline int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool SPLIT>
 int launch_gemm2_t(McmHandle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tout16,
-                   const GemmParams& p, cudaStream_t st) {
-    static bool attr_done = false;   // per instantiation; one device per process in practice
-    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI>;
-    if (!attr_done) {
-        MCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN, EPI>::kTotal));
-        attr_done = true;
-    }
+                   const CUtensorMap& ta_lo, const CUtensorMap& tb_lo, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_f16_tn_cta2_kernel<BN, EPI, SPLIT>;
+    MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(kern), Gemm2Smem<BN, EPI>::kTotal));
     const int tiles = p.m_tiles * p.n_tiles;
     const int clusters = std::min(tiles, h->num_sms / 2);   // persistent: one CTA pair per TPC
-    MCM_CUDA(h, launch_k(kern, dim3(2 * clusters), dim3(EpiTraits<EPI>::kThreads), Gemm2Smem<BN, EPI>::kTotal, st, 2, ta, tb, tout, tout16, p));
+    MCM_CUDA(h, launch_k(kern, dim3(2 * clusters), dim3(EpiTraits<EPI>::kThreads), Gemm2Smem<BN, EPI>::kTotal, st, 2, ta, tb, tout, tout16,
+                         ta_lo, tb_lo, p));
     h->launches++;
     return MCM_OK;
 }
@@ -297,6 +390,11 @@ struct GemmLnArgs {
     float2* stats_out = nullptr;
     int stats_ld = 0;
     int row_len = 1;
+    // split-precision mode: low halves of A / W (tensor maps) and of the fp16 outputs
+    const CUtensorMap* ta_lo = nullptr;
+    const CUtensorMap* tb_lo = nullptr;
+    op16_t* out_lo = nullptr;
+    op16_t* out16_lo = nullptr;
 };
 
 // C[M, N] = A[M, K] W[N, K]^T with fused epilogue.  M rows valid; A's tensor map covers >= ceil(M/128)*128 rows.
@@ -327,6 +425,10 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     p.eps = h->cfg.eps;
     p.out16 = ln.out16;
     p.stats_out = ln.stats_out;
+    p.out_lo = ln.out_lo;
+    p.out16_lo = ln.out16_lo;
+    const bool split = ln.ta_lo != nullptr;
+    if (split && !ln.tb_lo) return fail(h, MCM_EINVAL, "split GEMM needs both low-half operands");
     // Epilogue traffic that goes through TMA (fp16 outputs; the residual epilogue of EPI_BIAS_RESID_F32_LN_TMA) needs
     // tensor maps over the caller's buffers with exactly M rows, so that the TMA unit clips the last tile.
     CUtensorMap tout = ta, tout16 = ta;   // placeholders for the kinds that do not use them
@@ -334,8 +436,12 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     if (epi == EPI_BIAS_RESID_F32_LN) {
         // the LSU epilogue stays for long-K GEMMs (its time hides behind the main loop and it leaves 6 ring stages);
         // MCM_GEMM_RESID_TMA=0 / 1 forces one or the other (A/B runs)
+#ifdef MCM_DEBUG
         static const int force = [] { const char* e = getenv("MCM_GEMM_RESID_TMA"); return e ? atoi(e) : -1; }();
-        const bool use_tma = resid == out && (force >= 0 ? force != 0 : K <= 1024);
+#else
+        constexpr int force = -1;
+#endif
+        const bool use_tma = !split && resid == out && (force >= 0 ? force != 0 : K <= 1024);
         if (use_tma) epi = EPI_BIAS_RESID_F32_LN_TMA;
     }
     if (f16_out && MCM_GEMM_F16_TMA_STORE) {
@@ -355,8 +461,10 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
         p.trace = tr;
     }
 #endif
+#ifdef MCM_DEBUG
     static const int dbg_skip = [] { const char* e = getenv("MCM_GEMM_DBG_SKIP"); return e ? atoi(e) : 0; }();
     p.dbg_skip = dbg_skip;
+#endif
     ProfScope prof(h, prof_kind, st);
 #ifdef MCM_GEMM_TRACE
     struct TraceDump {
@@ -374,8 +482,22 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
         }
     } trace_dump{h, p.trace, st, M, N, K, epi};
 #endif
+    if (split) {
+        // the kinds the split-precision forward uses (the TMA residual epilogue and the plain-bias fp16 kinds have no split form)
+#define MCM_GEMM_SPLIT_CASE(E)                                                                                   \
+    if (epi == E)                                                                                               \
+        return bn == 256 ? launch_gemm2_t<256, E, true>(h, ta, tb, tout, tout16, *ln.ta_lo, *ln.tb_lo, p, st)   \
+                         : launch_gemm2_t<128, E, true>(h, ta, tb, tout, tout16, *ln.ta_lo, *ln.tb_lo, p, st);
+        MCM_GEMM_SPLIT_CASE(EPI_BIAS_RESID_F32)
+        MCM_GEMM_SPLIT_CASE(EPI_POS_F32)
+        MCM_GEMM_SPLIT_CASE(EPI_LN_F16)
+        MCM_GEMM_SPLIT_CASE(EPI_LN_QGELU_F16)
+        MCM_GEMM_SPLIT_CASE(EPI_BIAS_RESID_F32_LN)
+#undef MCM_GEMM_SPLIT_CASE
+        return fail(h, MCM_EINVAL, "GEMM epilogue %d has no split-precision form", epi);
+    }
 #define MCM_GEMM_CASE(E)                                                     \
-    if (epi == E) return bn == 256 ? launch_gemm2_t<256, E>(h, ta, tb, tout, tout16, p, st) : launch_gemm2_t<128, E>(h, ta, tb, tout, tout16, p, st);
+    if (epi == E) return bn == 256 ? launch_gemm2_t<256, E, false>(h, ta, tb, tout, tout16, ta, tb, p, st) : launch_gemm2_t<128, E, false>(h, ta, tb, tout, tout16, ta, tb, p, st);
     MCM_GEMM_CASE(EPI_BIAS_F16)
     MCM_GEMM_CASE(EPI_BIAS_QGELU_F16)
     MCM_GEMM_CASE(EPI_BIAS_RESID_F32)
@@ -421,25 +543,30 @@ int launch_layernorm(McmHandle* h, const float* x, const float* g, const float* 
     return MCM_OK;
 }
 
-int launch_attention_mma(McmHandle* h, const op16_t* qkv, op16_t* out, int b, int S, int H, cudaStream_t st) {
+// warp-level mma.sync attention: sequences beyond the tcgen05 kernel's 257 tokens, and (qkv_lo != nullptr) the
+// three-term attention of the split-precision mode
+int launch_attention_mma(McmHandle* h, const op16_t* qkv, const op16_t* qkv_lo, op16_t* out, op16_t* out_lo, int b, int S, int H,
+                         cudaStream_t st) {
+    const bool split = qkv_lo != nullptr;
     const int keys_pad = (S + 15) / 16 * 16;
-    const size_t smem = static_cast<size_t>(2) * keys_pad * kAttnLd * sizeof(op16_t);
+    const size_t smem = static_cast<size_t>(split ? 4 : 2) * keys_pad * kAttnLd * sizeof(op16_t);
     if (smem > 200 * 1024) return fail(h, MCM_EUNSUPPORTED, "sequence length %d too long for the attention kernel", S);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        MCM_CUDA(h, cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // without this the driver's default L1/shared split leaves room for ONE 60 KB CTA per SM
-        MCM_CUDA(h, cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared));
-        attr_smem = smem;
-    }
+    const void* fn = split ? reinterpret_cast<const void*>(attention_mma_kernel<true>) : reinterpret_cast<const void*>(attention_mma_kernel<false>);
+    bool first = true;
+    for (auto& e : h->smem_attr) first = first && e.first != fn;
+    MCM_CUDA(h, ensure_smem(h, fn, (int)smem));
+    if (first)   // without this the driver's default L1/shared split leaves room for ONE 60 KB CTA per SM
+        MCM_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int mtiles = (S + 15) / 16;
     int nwarps = (mtiles + 1) / 2;
     if (nwarps > 9) nwarps = 9;
     if (nwarps < 1) nwarps = 1;
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    MCM_CUDA(h, launch_k(attention_mma_kernel, dim3(b * H), dim3(nwarps * 32), smem, st, 1, qkv, out, S, H, keys_pad, scale_log2e));
+    if (split)
+        MCM_CUDA(h, launch_k(attention_mma_kernel<true>, dim3(b * H), dim3(nwarps * 32), smem, st, 1, qkv, qkv_lo, out, out_lo, S, H, keys_pad, scale_log2e));
+    else
+        MCM_CUDA(h, launch_k(attention_mma_kernel<false>, dim3(b * H), dim3(nwarps * 32), smem, st, 1, qkv, qkv_lo, out, out_lo, S, H, keys_pad, scale_log2e));
     h->launches++;
     return MCM_OK;
 }
@@ -448,7 +575,7 @@ int launch_attention_mma(McmHandle* h, const op16_t* qkv, op16_t* out, int b, in
 int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tx, const op16_t* qkv, op16_t* out,
                      int b, int S, int H, cudaStream_t st) {
     if (b <= 0) return MCM_OK;
-    if (h->attn_mma || S > kAtcMaxS) return launch_attention_mma(h, qkv, out, b, S, H, st);
+    if (h->attn_mma || S > kAtcMaxS) return launch_attention_mma(h, qkv, nullptr, out, nullptr, b, S, H, st);
     AtcParams p{};
     p.b = b;
     p.S = S;
@@ -467,11 +594,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     p.trace = trace_dev;
 #endif
     const int smem = atc_smem_bytes(p.keys_pad);
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        MCM_CUDA(h, cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_tcgen05_kernel), smem));
     const int items = p.pair_mode ? (b * H + 1) / 2 : b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
@@ -521,27 +644,36 @@ int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T,
 
 // images: fp32 NCHW already normalised (u8 == false) or uint8 NHWC straight from the decoder (u8 == true)
 int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st) {
+    const bool split = h->precision == MCM_PRECISION_SPLIT;
     {
         ProfScope prof(h, MCM_PROF_PATCHIFY, st);
         const size_t smem = patchify_smem_bytes(h->G, h->cfg.patch);
-        if (u8)
-            MCM_CUDA(h, launch_k(patchify_u8_kernel, dim3(b * h->G), dim3(256), smem, st, 1, static_cast<const uint8_t*>(images), h->patches,
-                                 h->G, h->cfg.patch, h->Kp, h->norm));
-        else
-            MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), smem, st, 1, static_cast<const float*>(images), h->patches,
-                                 h->G, h->cfg.patch, h->Kp));
+        for (int lo = 0; lo < (split ? 2 : 1); ++lo) {      // split-precision mode: a second pass writes the low halves
+            op16_t* dst = lo ? h->patches_lo : h->patches;
+            if (u8)
+                MCM_CUDA(h, launch_k(patchify_u8_kernel, dim3(b * h->G), dim3(256), smem, st, 1, static_cast<const uint8_t*>(images), dst,
+                                     h->G, h->cfg.patch, h->Kp, h->norm, lo));
+            else
+                MCM_CUDA(h, launch_k(patchify_kernel, dim3(b * h->G), dim3(256), smem, st, 1, static_cast<const float*>(images), dst,
+                                     h->G, h->cfg.patch, h->Kp, lo));
+            h->launches++;
+        }
     }
-    h->launches++;
+    GemmLnArgs sp;
+    if (split) {
+        sp.ta_lo = &h->tm_patches_lo;
+        sp.tb_lo = &h->tm_wpatch_lo;
+    }
     int rc = launch_gemm(h, MCM_PROF_GEMM_PATCH, h->tm_patches, h->tm_wpatch, b * h->Np, h->D, h->Kp, EPI_POS_F32, nullptr, h->x, nullptr,
-                         h->pos, h->Np, h->S, st);
+                         h->pos, h->Np, h->S, st, sp);
     if (rc) return rc;
     const int M = b * h->S;
     const int grid = (M + (kRowThreads / 32) - 1) / (kRowThreads / 32);
     ProfScope prof(h, MCM_PROF_EMBED_FINISH, st);
     rc = dispatch_vec(h, h->D, [&](auto vec) {
         constexpr int V = decltype(vec)::value;
-        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xh, h->stats, h->cls,
-                                   h->pos, h->pre_g, h->pre_b, M, h->S, h->cfg.eps));
+        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xh, split ? h->xh_lo : nullptr,
+                                   h->stats, h->cls, h->pos, h->pre_g, h->pre_b, M, h->S, h->cfg.eps));
     });
     if (rc) return rc;
     MCM_CUDA(h, cudaGetLastError());
@@ -555,6 +687,7 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
     int rc = launch_embed(h, images, u8, b, st);
     if (rc) return rc;
     const int M = b * h->S, D = h->D, F = h->F;
+    const bool split = h->precision == MCM_PRECISION_SPLIT;
     *pooled = h->x;
     *pooled_stride = static_cast<size_t>(h->S) * D;
     const int ld = static_cast<int>(h->m_pad);
@@ -563,18 +696,29 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
         const bool last = i + 1 == h->L;
         // consumer side of the LayerNorm fold: xh holds the raw fp16 rows of x, stats their partial sums
         // (one part after embed_finish, one per 128-column half tile after an out_proj / fc2 epilogue)
-        GemmLnArgs ln1, ln2, prod;
-        ln1.colsum = w.cqkv;
+        GemmLnArgs ln1, ln2, prod, out_a, fc2_a;
+        ln1.colsum = split ? w.cqkv_s : w.cqkv;
         ln1.stats_in = h->stats;
         ln1.stats_parts = i == 0 ? 1 : h->stats_parts;
         ln1.stats_ld = ld;
         ln1.row_len = D;
         ln2 = ln1;
-        ln2.colsum = w.c1;
+        ln2.colsum = split ? w.c1_s : w.c1;
         ln2.stats_parts = h->stats_parts;
         prod.out16 = h->xh;
         prod.stats_out = h->stats;
         prod.stats_ld = ld;
+        if (split) {     // every operand is an fp16 (hi, lo) pair (gemm_tcgen05.cuh, "Precision modes")
+            ln1.ta_lo = &h->tm_xh_lo;   ln1.tb_lo = &w.tm_wqkv_lo;  ln1.out_lo = h->qkv_lo;
+            ln2.ta_lo = &h->tm_xh_lo;   ln2.tb_lo = &w.tm_w1_lo;    ln2.out_lo = h->hid_lo;
+            prod.out16_lo = h->xh_lo;
+        }
+        out_a = prod;
+        fc2_a = prod;
+        if (split) {
+            out_a.ta_lo = &h->tm_attn_lo;  out_a.tb_lo = &w.tm_wo_lo;
+            fc2_a.ta_lo = &h->tm_hid_lo;   fc2_a.tb_lo = &w.tm_w2_lo;
+        }
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xh, w.tm_wqkv, M, 3 * D, D, EPI_LN_F16, w.dqkv, h->qkv, nullptr, nullptr, 0, 0, st, ln1))) return rc;
         if (last && h->cls_shortcut) {
             // only query row 0 of every image is consumed after this point (HF:685); the b CLS rows move to
@@ -582,22 +726,33 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
             {
                 ProfScope prof(h, MCM_PROF_ATTENTION, st);
                 MCM_CUDA(h, launch_k(attention_cls_kernel, dim3((b * h->H + kClsWarps - 1) / kClsWarps), dim3(kClsWarps * 32), 0,
-                                     st, 1, h->qkv, h->x, h->attn, h->x_cls, b, h->S, h->H, 0.125f));
+                                     st, 1, h->qkv, split ? h->qkv_lo : nullptr, h->x, h->attn, split ? h->attn_lo : nullptr, h->x_cls, b,
+                                     h->S, h->H, 0.125f));
             }
             h->launches++;
-            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st, prod))) return rc;
+            GemmLnArgs fc2_last;             // plain residual epilogue: no fp16 copy, no statistics
+            fc2_last.ta_lo = fc2_a.ta_lo;
+            fc2_last.tb_lo = fc2_a.tb_lo;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st, out_a))) return rc;
             if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, b, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
-            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, b, D, F, EPI_BIAS_RESID_F32, w.b2, h->x_cls, h->x_cls, nullptr, 0, 0, st))) return rc;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, b, D, F, EPI_BIAS_RESID_F32, w.b2, h->x_cls, h->x_cls, nullptr, 0, 0, st, fc2_last))) return rc;
             *pooled = h->x_cls;
             *pooled_stride = D;
             break;
         }
-        if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->tm_qkv_x, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x, h->x, nullptr, 0, 0, st, prod))) return rc;
+        if (split) {
+            if ((rc = launch_attention_mma(h, h->qkv, h->qkv_lo, h->attn, h->attn_lo, b, h->S, h->H, st))) return rc;
+        } else {
+            if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->tm_qkv_x, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
+        }
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x, h->x, nullptr, 0, 0, st, out_a))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, M, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
         // the last layer's output only feeds the pooled post-LN of the tail: no fp16 copy, no statistics
+        GemmLnArgs fc2_last;
+        fc2_last.ta_lo = fc2_a.ta_lo;
+        fc2_last.tb_lo = fc2_a.tb_lo;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, last ? EPI_BIAS_RESID_F32 : EPI_BIAS_RESID_F32_LN, w.b2,
-                              h->x, h->x, nullptr, 0, 0, st, last ? GemmLnArgs() : prod))) return rc;
+                              h->x, h->x, nullptr, 0, 0, st, last ? fc2_last : fc2_a))) return rc;
     }
     return MCM_OK;
 }
@@ -627,6 +782,7 @@ int dev_alloc(McmHandle* h, T** p, size_t n, bool zero) {
 struct Dest {
     float* f32 = nullptr;            // fp32 destination (also the fp32 master of a LayerNorm-folded weight), or
     op16_t* fp16 = nullptr;   // fp16 destination (converted)
+    op16_t* fp16_lo = nullptr;   // its low half (split-precision mode)
     int64_t rows = 0;
     int cols = 0, dst_ld = 0;
     int slot = -1;
@@ -655,11 +811,11 @@ const char* kLayerNames[16] = {"layer_norm1.weight", "layer_norm1.bias", "layer_
 bool resolve_key(McmHandle* h, const char* key, Dest* d) {
     const int D = h->D, F = h->F, P = h->P;
     auto f32 = [&](float* p, int64_t n, int slot) { d->f32 = p; d->rows = 1; d->cols = (int)n; d->slot = slot; return true; };
-    auto b16 = [&](op16_t* p, int64_t rows, int cols, int ld, int slot) {
-        d->fp16 = p; d->rows = rows; d->cols = cols; d->dst_ld = ld; d->slot = slot; return true;
+    auto b16 = [&](op16_t* p, op16_t* p_lo, int64_t rows, int cols, int ld, int slot) {
+        d->fp16 = p; d->fp16_lo = p_lo; d->rows = rows; d->cols = cols; d->dst_ld = ld; d->slot = slot; return true;
     };
     if (!strcmp(key, "vision_model.embeddings.class_embedding")) return f32(h->cls, D, SLOT_CLS);
-    if (!strcmp(key, "vision_model.embeddings.patch_embedding.weight")) return b16(h->wpatch, D, h->Kpatch, h->Kp, SLOT_PATCH);
+    if (!strcmp(key, "vision_model.embeddings.patch_embedding.weight")) return b16(h->wpatch, h->wpatch_lo, D, h->Kpatch, h->Kp, SLOT_PATCH);
     if (!strcmp(key, "vision_model.embeddings.position_embedding.weight")) return f32(h->pos, (int64_t)h->S * D, SLOT_POS);
     if (!strcmp(key, "vision_model.pre_layrnorm.weight")) return f32(h->pre_g, D, SLOT_PRE_G);
     if (!strcmp(key, "vision_model.pre_layrnorm.bias")) return f32(h->pre_b, D, SLOT_PRE_B);
@@ -686,11 +842,11 @@ bool resolve_key(McmHandle* h, const char* key, Dest* d) {
         case 7: return f32(w.bqkv + D, D, slot);
         case 8: return f32(w.wqkv32 + (size_t)2 * D * D, (int64_t)D * D, slot);
         case 9: return f32(w.bqkv + 2 * D, D, slot);
-        case 10: return b16(w.wo, D, D, D, slot);
+        case 10: return b16(w.wo, w.wo_lo, D, D, D, slot);
         case 11: return f32(w.bo, D, slot);
         case 12: return f32(w.w132, (int64_t)F * D, slot);
         case 13: return f32(w.b1, F, slot);
-        case 14: return b16(w.w2, D, F, F, slot);
+        case 14: return b16(w.w2, w.w2_lo, D, F, F, slot);
         case 15: return f32(w.b2, D, slot);
     }
     return false;
@@ -721,6 +877,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
                     cfg->image_size, cfg->patch);
     if (cfg->width <= 0 || cfg->width % 128 != 0 || cfg->width > 1024)
         return fail(nullptr, MCM_EUNSUPPORTED, "width %d must be a multiple of 128, at most 1024", cfg->width);
+    if (2 * (cfg->width / gemm_block_n(cfg->width)) > kMaxStatsParts)
+        return fail(nullptr, MCM_EUNSUPPORTED, "width %d: the LayerNorm fold keeps at most %d partial row statistics (width must be a "
+                    "multiple of 256, or at most 512)", cfg->width, kMaxStatsParts);
     if (cfg->heads <= 0 || cfg->width != cfg->heads * 64)
         return fail(nullptr, MCM_EUNSUPPORTED, "width / heads must be 64 (got %d / %d)", cfg->width, cfg->heads);
     if (cfg->mlp <= 0 || cfg->mlp % 128 != 0) return fail(nullptr, MCM_EUNSUPPORTED, "mlp %d must be a multiple of 128", cfg->mlp);
@@ -740,7 +899,9 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     if (prop.major != 10)
         return fail(nullptr, MCM_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
                     prop.major, prop.minor);
-    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, MCM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    DeviceGuard guard(cfg->device);
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != cfg->device) return fail(nullptr, MCM_ECUDA, "cudaSetDevice(%d) failed", cfg->device);
 
     McmHandle* h = new McmHandle();
     h->cfg = *cfg;
@@ -770,6 +931,12 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     } while (0)
 
     MCM_TRY(dev_alloc(h, &h->wpatch, (size_t)D * h->Kp, true));
+    MCM_TRY(dev_alloc(h, &h->wpatch_lo, (size_t)D * h->Kp, true));
+    {
+        cudaError_t ee = cudaEventCreateWithFlags(&h->ev_busy, cudaEventDisableTiming);
+        if (ee != cudaSuccess) MCM_TRY(fail(h, MCM_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(ee)));
+    }
+    MCM_TRY(dev_alloc(h, &h->t_scores, (size_t)cfg->max_batch, false));
     MCM_TRY(dev_alloc(h, &h->cls, D, true));
     MCM_TRY(dev_alloc(h, &h->pos, (size_t)h->S * D, true));
     MCM_TRY(dev_alloc(h, &h->pre_g, D, true));
@@ -783,6 +950,12 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         MCM_TRY(dev_alloc(h, &w.wo, (size_t)D * D, false));
         MCM_TRY(dev_alloc(h, &w.w1, (size_t)F * D, false));
         MCM_TRY(dev_alloc(h, &w.w2, (size_t)D * F, false));
+        MCM_TRY(dev_alloc(h, &w.wqkv_lo, (size_t)3 * D * D, false));
+        MCM_TRY(dev_alloc(h, &w.wo_lo, (size_t)D * D, false));
+        MCM_TRY(dev_alloc(h, &w.w1_lo, (size_t)F * D, false));
+        MCM_TRY(dev_alloc(h, &w.w2_lo, (size_t)D * F, false));
+        MCM_TRY(dev_alloc(h, &w.cqkv_s, (size_t)3 * D, false));
+        MCM_TRY(dev_alloc(h, &w.c1_s, F, false));
         MCM_TRY(dev_alloc(h, &w.wqkv32, (size_t)3 * D * D, false));
         MCM_TRY(dev_alloc(h, &w.w132, (size_t)F * D, false));
         MCM_TRY(dev_alloc(h, &w.cqkv, (size_t)3 * D, false));
@@ -803,8 +976,13 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
         MCM_TRY(make_tmap(h, &w.tm_wo, w.wo, D, D, bnD));
         MCM_TRY(make_tmap(h, &w.tm_w1, w.w1, F, D, bnF));
         MCM_TRY(make_tmap(h, &w.tm_w2, w.w2, D, F, bnD));
+        MCM_TRY(make_tmap(h, &w.tm_wqkv_lo, w.wqkv_lo, 3 * D, D, bn3D));
+        MCM_TRY(make_tmap(h, &w.tm_wo_lo, w.wo_lo, D, D, bnD));
+        MCM_TRY(make_tmap(h, &w.tm_w1_lo, w.w1_lo, F, D, bnF));
+        MCM_TRY(make_tmap(h, &w.tm_w2_lo, w.w2_lo, D, F, bnD));
     }
     MCM_TRY(make_tmap(h, &h->tm_wpatch, h->wpatch, D, h->Kp, gemm_block_n(D) / 2));
+    MCM_TRY(make_tmap(h, &h->tm_wpatch_lo, h->wpatch_lo, D, h->Kp, gemm_block_n(D) / 2));
     h->loaded.assign(SLOT_GLOBALS + 16 * h->L, 0);
     h->stage_elems = (size_t)std::max(std::max((size_t)F * D, (size_t)D * h->Kpatch), std::max((size_t)h->S * D, (size_t)h->P * D));
     MCM_TRY(dev_alloc(h, &h->stage, h->stage_elems, false));
@@ -827,11 +1005,13 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(make_tmap(h, &h->tm_attn, h->attn, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_hid, h->hid, h->m_pad, F, kGemmBlockM));
     {
-        const char* e = getenv("MCM_ATTN_MMA");
+#ifdef MCM_DEBUG
+        const char* e = getenv("MCM_ATTN_MMA");      // A/B switch: warp-level mma.sync attention for every shape
         h->attn_mma = e && e[0] == '1';
+#endif
         if (h->S <= kAtcMaxS) {
             MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
-            MCM_TRY(make_tmap(h, &h->tm_qkv_kv, h->qkv, h->m_pad, 3 * D, atc_kv_box_rows(h->S)));
+            MCM_TRY(make_tmap_kv(h, &h->tm_qkv_kv, h->qkv, cfg->max_batch, h->S, 3 * D, atc_kv_box_rows(h->S)));
             MCM_TRY(make_tmap(h, &h->tm_qkv_x, h->qkv, h->m_pad, 3 * D, 8));
         }
     }
@@ -842,14 +1022,20 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
 
 void mcm_destroy(McmHandle* h) {
     if (!h) return;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
     auto fr = [](void* p) { if (p) cudaFree(p); };
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.first);
+    h->graphs.clear();
+    if (h->ev_busy) cudaEventDestroy(h->ev_busy);
+    fr(h->t_scores); fr(h->wpatch_lo);
+    fr(h->patches_lo); fr(h->xh_lo); fr(h->qkv_lo); fr(h->attn_lo); fr(h->hid_lo);
     fr(h->wpatch); fr(h->cls); fr(h->pos); fr(h->pre_g); fr(h->pre_b); fr(h->post_g); fr(h->post_b); fr(h->wproj);
     for (auto& w : h->layers) {
         fr(w.wqkv); fr(w.wo); fr(w.w1); fr(w.w2); fr(w.bqkv); fr(w.bo); fr(w.b1); fr(w.b2);
         fr(w.ln1g); fr(w.ln1b); fr(w.ln2g); fr(w.ln2b);
         fr(w.wqkv32); fr(w.w132); fr(w.cqkv); fr(w.dqkv); fr(w.c1); fr(w.d1);
+        fr(w.wqkv_lo); fr(w.wo_lo); fr(w.w1_lo); fr(w.w2_lo); fr(w.cqkv_s); fr(w.c1_s);
     }
     fr(h->stats);
     fr(h->stage); fr(h->bank); fr(h->patches); fr(h->x); fr(h->xh); fr(h->qkv); fr(h->attn); fr(h->hid);
@@ -880,12 +1066,12 @@ int mcm_load_weight(McmHandle* h, const char* key, const float* data, int64_t nu
     if (!resolve_key(h, key, &d)) return MCM_OK;  // not part of the vision path
     const int64_t want = d.rows * d.cols;
     if (numel != want) return fail(h, MCM_EINVAL, "%s: expected %lld elements, got %lld", key, (long long)want, (long long)numel);
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     if (d.f32) {
         MCM_CUDA(h, cudaMemcpy(d.f32, data, want * sizeof(float), cudaMemcpyDefault));
     } else {
         MCM_CUDA(h, cudaMemcpy(h->stage, data, want * sizeof(float), cudaMemcpyDefault));
-        convert_rows_f16_kernel<<<1024, 256>>>(h->stage, d.fp16, d.rows, d.cols, d.dst_ld);
+        convert_rows_f16_kernel<<<1024, 256>>>(h->stage, d.fp16, d.fp16_lo, d.rows, d.cols, d.dst_ld);
         MCM_CUDA(h, cudaGetLastError());
         MCM_CUDA(h, cudaDeviceSynchronize());
     }
@@ -909,11 +1095,13 @@ int mcm_finalize_weights(McmHandle* h) {
         const int li = (int)(i - SLOT_GLOBALS) / 16, which = (int)(i - SLOT_GLOBALS) % 16;
         return fail(h, MCM_ESTATE, "weight vision_model.encoder.layers.%d.%s was never loaded", li, kLayerNames[which]);
     }
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     // LayerNorm fold (gemm_tcgen05.cuh): W' = fp16(gamma o W), c = row sums of W', d = beta @ W^T + b
+    // (+ the low halves of W' and the row sums of hi + lo for the split-precision mode)
     for (auto& w : h->layers) {
-        fold_ln_weight_kernel<<<(3 * h->D + 7) / 8, 256>>>(w.wqkv32, w.ln1g, w.ln1b, w.bqkv, w.wqkv, w.cqkv, w.dqkv, 3 * h->D, h->D);
-        fold_ln_weight_kernel<<<(h->F + 7) / 8, 256>>>(w.w132, w.ln2g, w.ln2b, w.b1, w.w1, w.c1, w.d1, h->F, h->D);
+        fold_ln_weight_kernel<<<(3 * h->D + 7) / 8, 256>>>(w.wqkv32, w.ln1g, w.ln1b, w.bqkv, w.wqkv, w.cqkv, w.dqkv, 3 * h->D, h->D,
+                                                          w.wqkv_lo, w.cqkv_s);
+        fold_ln_weight_kernel<<<(h->F + 7) / 8, 256>>>(w.w132, w.ln2g, w.ln2b, w.b1, w.w1, w.c1, w.d1, h->F, h->D, w.w1_lo, w.c1_s);
     }
     MCM_CUDA(h, cudaGetLastError());
     MCM_CUDA(h, cudaDeviceSynchronize());
@@ -924,8 +1112,10 @@ int mcm_finalize_weights(McmHandle* h) {
 int mcm_set_text_bank(McmHandle* h, const float* bank, int32_t K, int32_t already_unit) {
     if (!h || !bank) return fail(h, MCM_EINVAL, "mcm_set_text_bank: NULL argument");
     if (K <= 0) return fail(h, MCM_EINVAL, "K must be positive (got %d)", K);
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     MCM_CUDA(h, cudaDeviceSynchronize());
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.first);     // captured graphs point at the old bank / logits buffers
+    h->graphs.clear();
     if (h->bank) { cudaFree(h->bank); h->bank = nullptr; h->K = 0; }
     if (h->t_logit) { cudaFree(h->t_logit); h->t_logit = nullptr; }
     int rc = dev_alloc(h, &h->bank, (size_t)K * h->P, false);
@@ -945,16 +1135,102 @@ int mcm_set_text_bank(McmHandle* h, const float* bank, int32_t K, int32_t alread
 
 namespace {
 
+// feats [b,P] (un-normalised projected features) -> Mahalanobis scores
+int launch_maha(McmHandle* h, float* feats, int b, float* scores, cudaStream_t st) {
+    ProfScope prof(h, MCM_PROF_TAIL, st);
+    if (h->maha_normalize) MCM_CUDA(h, launch_k(normalize_rows_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, feats, b, h->P));
+    dim3 g1((h->P + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
+    MCM_CUDA(h, launch_k(sgemm_tn_kernel, g1, dim3(256), 0, st, 1, static_cast<const float*>(feats), static_cast<const float*>(h->maha_lt),
+                         h->maha_g, b, h->P, h->P));
+    MCM_CUDA(h, launch_k(maha_min_dist_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, static_cast<const float*>(h->maha_g),
+                         static_cast<const float*>(h->maha_c), h->P, h->maha_K, b, scores));
+    h->launches += h->maha_normalize ? 3 : 2;
+    return MCM_OK;
+}
+
+// ---- one forward = tower + tail, ordered against the handle's previous forward, optionally replayed from a CUDA graph ----
+enum FwdMode { FWD_FEATURES = 0, FWD_SCORE = 1, FWD_MAHA = 2 };
+
+// the launches of one forward; `feats` / `scores` are where the tail writes
+int enqueue_forward(McmHandle* h, const void* images, bool u8, int b, int mode, float T, int kind, float* feats, float* scores,
+                    cudaStream_t st) {
+    const float* pooled = nullptr;
+    size_t stride = 0;
+    int rc = forward_tower(h, images, u8, b, st, &pooled, &stride);
+    if (rc) return rc;
+    if (mode == FWD_FEATURES) return launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, feats, nullptr, st);
+    if (mode == FWD_SCORE) return launch_tail(h, pooled, stride, b, T, kind, nullptr, scores, st);
+    if ((rc = launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, h->t_feat, nullptr, st))) return rc;
+    return launch_maha(h, h->t_feat, b, scores, st);
+}
+
+// Every forward of a handle uses the same activation workspace: wait for the previous one (which may have been
+// enqueued on another stream -- the caller's, or the handle's own copy / compute streams) before touching it.
+void forward_begin(McmHandle* h, cudaStream_t st) {
+    if (h->busy_recorded && h->busy_stream != st) cudaStreamWaitEvent(st, h->ev_busy, 0);
+}
+void forward_end(McmHandle* h, cudaStream_t st) {
+    cudaEventRecord(h->ev_busy, st);
+    h->busy_recorded = true;
+    h->busy_stream = st;
+}
+
+int run_forward(McmHandle* h, const void* images, bool u8, int b, int mode, float T, int kind, float* out, cudaStream_t st) {
+    forward_begin(h, st);
+    int rc = MCM_OK;
+    const size_t out_elems = mode == FWD_FEATURES ? (size_t)b * h->P : (size_t)b;
+    if (h->use_graph && !h->prof_on) {
+        // the graph writes into handle-owned buffers (t_feat / t_scores); a device-to-device copy behind it delivers
+        // the result, so one graph serves every destination pointer
+        float* g_out = mode == FWD_FEATURES ? h->t_feat : h->t_scores;
+        uint32_t t_bits;
+        memcpy(&t_bits, &T, sizeof t_bits);
+        const McmHandle::GraphKey key{images, u8 ? 1 : 0, b, mode, kind, h->precision, h->cls_shortcut ? 1 : 0, h->K, t_bits};
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            // warm pass outside the capture: first-use attribute calls / tensor-map encodes happen here
+            rc = enqueue_forward(h, images, u8, b, mode, T, kind, mode == FWD_FEATURES ? g_out : nullptr,
+                                 mode == FWD_FEATURES ? nullptr : g_out, st);
+            if (rc) return rc;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            int64_t n_kernels = 0;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const int64_t launches0 = h->launches;
+                rc = enqueue_forward(h, images, u8, b, mode, T, kind, mode == FWD_FEATURES ? g_out : nullptr,
+                                     mode == FWD_FEATURES ? nullptr : g_out, st);
+                n_kernels = h->launches - launches0;
+                h->launches = launches0;      // recorded, not launched
+                e = cudaStreamEndCapture(st, &graph);
+                if (rc == MCM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (rc) return rc;
+            if (e != cudaSuccess) return fail(h, MCM_ECUDA, "CUDA graph capture of the forward failed: %s", cudaGetErrorString(e));
+            if (h->graphs.size() >= 64) {     // callers that never reuse an input buffer: bounded
+                for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.first);
+                h->graphs.clear();
+            }
+            it = h->graphs.emplace(key, std::make_pair(exec, n_kernels)).first;
+        }
+        MCM_CUDA(h, cudaGraphLaunch(it->second.first, st));
+        h->launches += it->second.second;
+        MCM_CUDA(h, cudaMemcpyAsync(out, g_out, out_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+        rc = enqueue_forward(h, images, u8, b, mode, T, kind, mode == FWD_FEATURES ? out : nullptr, mode == FWD_FEATURES ? nullptr : out, st);
+    }
+    forward_end(h, st);
+    return rc;
+}
+
 int image_features_any(McmHandle* h, const void* images, bool u8, int32_t b, float* feats, void* stream) {
     int rc = check_ready(h, b, false);
     if (rc) return rc;
     if (b == 0) return MCM_OK;
     if (!images || !feats) return fail(h, MCM_EINVAL, "mcm_image_features: NULL buffer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float* pooled = nullptr;
-    size_t stride = 0;
-    if ((rc = forward_tower(h, images, u8, b, st, &pooled, &stride))) return rc;
-    return launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, feats, nullptr, st);
+    DeviceGuard guard(h->cfg.device);
+    return run_forward(h, images, u8, b, FWD_FEATURES, 1.0f, SCORE_MCM, feats, static_cast<cudaStream_t>(stream));
 }
 
 int score_any(McmHandle* h, const void* images, bool u8, int32_t b, float T, int32_t kind, float* scores, void* stream) {
@@ -964,11 +1240,8 @@ int score_any(McmHandle* h, const void* images, bool u8, int32_t b, float T, int
     if (!images || !scores) return fail(h, MCM_EINVAL, "mcm_score: NULL buffer");
     if (!(T > 0.f)) return fail(h, MCM_EINVAL, "temperature must be positive (got %g)", (double)T);
     if (kind < MCM_SCORE_MCM || kind > MCM_SCORE_VAR) return fail(h, MCM_EINVAL, "unknown score kind %d", kind);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float* pooled = nullptr;
-    size_t stride = 0;
-    if ((rc = forward_tower(h, images, u8, b, st, &pooled, &stride))) return rc;
-    return launch_tail(h, pooled, stride, b, T, kind, nullptr, scores, st);
+    DeviceGuard guard(h->cfg.device);
+    return run_forward(h, images, u8, b, FWD_SCORE, T, kind, scores, static_cast<cudaStream_t>(stream));
 }
 
 int score_stream_host_any(McmHandle* h, const void* images_host_v, bool u8, int64_t n, int32_t batch, float T, int32_t kind,
@@ -1004,7 +1277,7 @@ int mcm_resize_crop_u8(McmHandle* h, const uint8_t* src, const int64_t* offsets,
     if (!h) return MCM_EINVAL;
     if (n == 0) return MCM_OK;
     if (n < 0 || !src || !offsets || !hs || !ws || !dst) return fail(h, MCM_EINVAL, "mcm_resize_crop_u8: bad argument");
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int size = h->cfg.image_size;
     RcPlan plan;
@@ -1062,25 +1335,11 @@ int mcm_dbg_resize_tables(int32_t h, int32_t w, int32_t size, int32_t* ksize2, i
     return MCM_OK;
 }
 
-namespace {
-// feats [b,P] (un-normalised projected features) -> Mahalanobis scores
-int launch_maha(McmHandle* h, float* feats, int b, float* scores, cudaStream_t st) {
-    ProfScope prof(h, MCM_PROF_TAIL, st);
-    if (h->maha_normalize) MCM_CUDA(h, launch_k(normalize_rows_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, feats, b, h->P));
-    dim3 g1((h->P + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
-    MCM_CUDA(h, launch_k(sgemm_tn_kernel, g1, dim3(256), 0, st, 1, static_cast<const float*>(feats), static_cast<const float*>(h->maha_lt),
-                         h->maha_g, b, h->P, h->P));
-    MCM_CUDA(h, launch_k(maha_min_dist_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, static_cast<const float*>(h->maha_g),
-                         static_cast<const float*>(h->maha_c), h->P, h->maha_K, b, scores));
-    h->launches += h->maha_normalize ? 3 : 2;
-    return MCM_OK;
-}
-}  // namespace
 
 int mcm_set_maha(McmHandle* h, const float* lt, const float* centres, int32_t K, int32_t normalize) {
     if (!h || !lt || !centres) return fail(h, MCM_EINVAL, "mcm_set_maha: NULL argument");
     if (K <= 0) return fail(h, MCM_EINVAL, "K must be positive (got %d)", K);
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     MCM_CUDA(h, cudaDeviceSynchronize());
     auto fr = [](float*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(h->maha_lt); fr(h->maha_c); fr(h->maha_g);
@@ -1102,12 +1361,8 @@ int mcm_maha_score(McmHandle* h, const float* images, int32_t b, float* scores, 
     if (h->maha_K <= 0) return fail(h, MCM_ESTATE, "Mahalanobis statistics are not set (call mcm_set_maha)");
     if (b == 0) return MCM_OK;
     if (!images || !scores) return fail(h, MCM_EINVAL, "mcm_maha_score: NULL buffer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float* pooled = nullptr;
-    size_t stride = 0;
-    if ((rc = forward_tower(h, images, false, b, st, &pooled, &stride))) return rc;
-    if ((rc = launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, h->t_feat, nullptr, st))) return rc;
-    return launch_maha(h, h->t_feat, b, scores, st);
+    DeviceGuard guard(h->cfg.device);
+    return run_forward(h, images, false, b, FWD_MAHA, 1.0f, SCORE_MCM, scores, static_cast<cudaStream_t>(stream));
 }
 
 int mcm_dbg_maha_from_features(McmHandle* h, const float* feats, int32_t b, float* scores, void* stream) {
@@ -1126,7 +1381,7 @@ int mcm_score_stream_host_images(McmHandle* h, const uint8_t* packed_host, const
     if (n == 0) return MCM_OK;
     if (n < 0 || batch <= 0) return fail(h, MCM_EINVAL, "n must be >= 0 and batch positive");
     if (!packed_host || !offsets || !hs || !ws || !scores_host) return fail(h, MCM_EINVAL, "mcm_score_stream_host_images: NULL argument");
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     const size_t out_elems = (size_t)3 * h->cfg.image_size * h->cfg.image_size;
     if (!h->s_copy) {
         MCM_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
@@ -1206,7 +1461,7 @@ int score_stream_host_any(McmHandle* h, const void* images_host_v, bool u8, int6
     if (n == 0) return MCM_OK;
     if (n < 0 || batch <= 0) return fail(h, MCM_EINVAL, "n must be >= 0 and batch positive");
     if (!images_host_v || !scores_host) return fail(h, MCM_EINVAL, "mcm_score_stream_host: NULL buffer");
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     const size_t img_elems = (size_t)3 * h->cfg.image_size * h->cfg.image_size;
     const size_t esz = u8 ? 1 : sizeof(float);
     const uint8_t* images_host = static_cast<const uint8_t*>(images_host_v);
@@ -1257,6 +1512,30 @@ int mcm_set_option(McmHandle* h, int32_t option, int32_t value) {
     if (!h) return MCM_EINVAL;
     switch (option) {
         case MCM_OPT_CLS_SHORTCUT: h->cls_shortcut = value != 0; return MCM_OK;
+        case MCM_OPT_CUDA_GRAPH: h->use_graph = value != 0; return MCM_OK;
+        case MCM_OPT_PRECISION: {
+            if (value != MCM_PRECISION_FP16 && value != MCM_PRECISION_SPLIT) return fail(h, MCM_EINVAL, "unknown precision mode %d", value);
+            if (value == MCM_PRECISION_SPLIT && !h->hid_lo) {
+                // low halves of the fp16 activation buffers + their tensor maps, on first use
+                DeviceGuard guard(h->cfg.device);
+                MCM_CUDA(h, cudaDeviceSynchronize());
+                const int D = h->D;
+                int rc;
+                if ((rc = dev_alloc(h, &h->patches_lo, (size_t)h->mp_pad * h->Kp, true))) return rc;
+                if ((rc = dev_alloc(h, &h->xh_lo, (size_t)h->m_pad * D, true))) return rc;
+                if ((rc = dev_alloc(h, &h->qkv_lo, (size_t)h->m_pad * 3 * D, true))) return rc;
+                if ((rc = dev_alloc(h, &h->attn_lo, (size_t)h->m_pad * D, true))) return rc;
+                if ((rc = make_tmap(h, &h->tm_patches_lo, h->patches_lo, h->mp_pad, h->Kp, kGemmBlockM))) return rc;
+                if ((rc = make_tmap(h, &h->tm_xh_lo, h->xh_lo, h->m_pad, D, kGemmBlockM))) return rc;
+                if ((rc = make_tmap(h, &h->tm_attn_lo, h->attn_lo, h->m_pad, D, kGemmBlockM))) return rc;
+                op16_t* hl = nullptr;
+                if ((rc = dev_alloc(h, &hl, (size_t)h->m_pad * h->F, true))) return rc;
+                if ((rc = make_tmap(h, &h->tm_hid_lo, hl, h->m_pad, h->F, kGemmBlockM))) { cudaFree(hl); return rc; }
+                h->hid_lo = hl;     // set last: marks the whole set as complete
+            }
+            h->precision = value;
+            return MCM_OK;
+        }
         default: return fail(h, MCM_EINVAL, "unknown option %d", option);
     }
 }
@@ -1269,7 +1548,7 @@ int mcm_profile_enable(McmHandle* h, int32_t on) {
 
 int mcm_profile_read(McmHandle* h, double* ms, int64_t* counts, int32_t reset) {
     if (!h) return MCM_EINVAL;
-    MCM_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     MCM_CUDA(h, cudaDeviceSynchronize());
     for (auto& r : h->prof_recs) {
         float t = 0.f;
@@ -1302,6 +1581,61 @@ int mcm_dbg_gemm(McmHandle* h, const void* a, const void* w, const float* bias, 
     if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
     if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / 2))) return rc;
     return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, epi, bias, out, resid, nullptr, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int mcm_dbg_gemm_split(McmHandle* h, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                       const float* resid, float* out, int32_t M, int32_t N, int32_t K, void* stream) {
+    if (!h || !a_hi || !a_lo || !w_hi || !w_lo || !bias || !resid || !out) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_split: NULL argument");
+    if (M <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_split: M must be positive");
+    if (N % 128 != 0 || K % 64 != 0) return fail(h, MCM_EUNSUPPORTED, "mcm_dbg_gemm_split: N %% 128 and K %% 64 must be 0");
+    DeviceGuard guard(h->cfg.device);
+    CUtensorMap ta, tb, tal, tbl;
+    int rc;
+    if ((rc = make_tmap(h, &ta, a_hi, M, K, kGemmBlockM))) return rc;
+    if ((rc = make_tmap(h, &tal, a_lo, M, K, kGemmBlockM))) return rc;
+    if ((rc = make_tmap(h, &tb, w_hi, N, K, gemm_block_n(N) / 2))) return rc;
+    if ((rc = make_tmap(h, &tbl, w_lo, N, K, gemm_block_n(N) / 2))) return rc;
+    GemmLnArgs sp;
+    sp.ta_lo = &tal;
+    sp.tb_lo = &tbl;
+    return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, EPI_BIAS_RESID_F32, bias, out, resid, nullptr, 0, 0,
+                       static_cast<cudaStream_t>(stream), sp);
+}
+
+int mcm_dbg_attention_split(McmHandle* h, const void* qkv_hi, const void* qkv_lo, void* o_hi, void* o_lo, int32_t b, int32_t S,
+                            int32_t H, void* stream) {
+    if (!h || !qkv_hi || !qkv_lo || !o_hi || !o_lo) return fail(h, MCM_EINVAL, "mcm_dbg_attention_split: NULL argument");
+    if (b <= 0 || S <= 0 || H <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_attention_split: b, S, H must be positive");
+    DeviceGuard guard(h->cfg.device);
+    return launch_attention_mma(h, static_cast<const op16_t*>(qkv_hi), static_cast<const op16_t*>(qkv_lo), static_cast<op16_t*>(o_hi),
+                                static_cast<op16_t*>(o_lo), b, S, H, static_cast<cudaStream_t>(stream));
+}
+
+// ncclAllGather, resolved at run time from the NCCL the process already uses (no link-time dependency: the library
+// must load on boxes and in processes that never touch NCCL)
+int mcm_allgather_scores(McmHandle* h, void* nccl_comm, const float* local_dev, int32_t n_local_padded, float* all_dev, void* stream) {
+    if (!h || !nccl_comm || !local_dev || !all_dev) return fail(h, MCM_EINVAL, "mcm_allgather_scores: NULL argument");
+    if (n_local_padded <= 0) return fail(h, MCM_EINVAL, "mcm_allgather_scores: n_local_padded must be positive");
+    typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    typedef const char* (*ErrStrFn)(int);
+    static AllGatherFn fn = nullptr;
+    static ErrStrFn errstr = nullptr;
+    if (!fn) {
+        void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+        void* lib = nullptr;
+        if (!sym) {
+            lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy already mapped into the process (torch's)
+            if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+            if (lib) sym = dlsym(lib, "ncclAllGather");
+        }
+        if (!sym) return fail(h, MCM_EUNSUPPORTED, "mcm_allgather_scores: no NCCL in this process and libnccl.so.2 cannot be loaded");
+        fn = reinterpret_cast<AllGatherFn>(sym);
+        errstr = reinterpret_cast<ErrStrFn>(lib ? dlsym(lib, "ncclGetErrorString") : dlsym(RTLD_DEFAULT, "ncclGetErrorString"));
+    }
+    DeviceGuard guard(h->cfg.device);
+    const int r = fn(local_dev, all_dev, static_cast<size_t>(n_local_padded), /*ncclFloat32*/ 7, nccl_comm, static_cast<cudaStream_t>(stream));
+    if (r != 0) return fail(h, MCM_ECUDA, "ncclAllGather failed: %s", errstr ? errstr(r) : "unknown NCCL error");
+    return MCM_OK;
 }
 
 int mcm_dbg_fold_ln(McmHandle* h, const float* w, const float* gamma, const float* beta, const float* bias, void* w16, float* c,
@@ -1365,7 +1699,7 @@ int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t
     if (S <= kAtcMaxS && !h->attn_mma) {
         int rc;
         if ((rc = make_tmap(h, &tq, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 128))) return rc;
-        if ((rc = make_tmap(h, &tkv, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, atc_kv_box_rows(S)))) return rc;
+        if ((rc = make_tmap_kv(h, &tkv, qkv, static_cast<uint64_t>(b), static_cast<uint64_t>(S), 3ull * H * 64, atc_kv_box_rows(S)))) return rc;
         if ((rc = make_tmap(h, &tx, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 8))) return rc;
     }
     return launch_attention(h, tq, tkv, tx, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,

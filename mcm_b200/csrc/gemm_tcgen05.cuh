@@ -52,10 +52,30 @@ struct GemmParams {
     float eps;
     op16_t* out16;           // EPI_BIAS_RESID_F32_LN: fp16 copy of out (the next projection's A operand)
     float2* stats_out;       // EPI_BIAS_RESID_F32_LN: [2 * n_tiles][stats_ld]
+    // ---- split-fp16 precision mode (SPLIT kernels only; see "Precision modes" below) ----
+    op16_t* out_lo;          // fp16-output epilogues: low half of out  (out + out_lo carry ~22 significant bits)
+    op16_t* out16_lo;        // EPI_BIAS_RESID_F32_LN: low half of out16
     long long* trace;        // -DMCM_GEMM_TRACE builds: [8] cycle counters summed over CTAs (see tools/gemm_trace.py)
-    int dbg_skip;            // timing experiments only (env MCM_GEMM_DBG_SKIP): 1 no global stores, 2 no staging either,
-                             // 4 no TMEM drain at all, 8 no residual loads
+#ifdef MCM_DEBUG
+    int dbg_skip;            // timing experiments only (env MCM_GEMM_DBG_SKIP, -DMCM_DEBUG builds): 1 no global stores,
+                             // 2 no staging either, 4 no TMEM drain at all, 8 no residual loads
+#endif
 };
+
+#ifdef MCM_DEBUG
+#define MCM_DBG_SKIP(p, bit) ((p).dbg_skip & (bit))
+#else
+#define MCM_DBG_SKIP(p, bit) 0
+#endif
+
+// Precision modes.
+//   fast (default): every tensor-core operand is ONE fp16 value (11-bit significand); per-GEMM relative error ~7e-4.
+//   split (MCM_OPT_PRECISION = 1): every operand is a PAIR of fp16 values, x = hi + lo with hi = fp16(x) and
+//     lo = fp16(x - hi) (~22 significant bits), and every product is the three-term sum
+//         A W^T  ~=  A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T            (the dropped A_lo W_lo^T term is ~2^-22)
+//     accumulated in the same fp32 TMEM tile: the k-loop of a SPLIT kernel walks the k-blocks three times over
+//     (hi, hi), (lo, hi), (hi, lo) operand tiles.  fp32-class results at 3x the tensor work; this is the mode in which
+//     AUROC / FPR95 agree with the fp32 reference to the last counted image.
 
 constexpr int kGemmBlockM = 128;   // rows per CTA (256 per CTA pair)
 constexpr int kGemmBlockK = 64;    // 64 fp16 = one 128-byte swizzle row
@@ -65,6 +85,16 @@ constexpr int kGemmBlockK = 64;    // 64 fp16 = one 128-byte swizzle row
 // 2^-11: the absolute error stays below half an fp16 ulp of |v|, i.e. below the rounding of the fp16 output itself).
 // The fc1 epilogue is MUFU-bound with the two-op form (ex2 + rcp): 7.5 k cycles per 256 x 256 tile against a
 // 6.1 k-cycle main loop.  -DMCM_GELU_EXACT restores ex2 + rcp (A/B builds).
+// exact form for the split-precision mode: ex2.approx (2 ulp) and a full-precision division
+__device__ __forceinline__ float quick_gelu_precise(float v) { return __fdiv_rn(v, 1.0f + __expf(-1.702f * v)); }
+
+// x -> (hi, lo) fp16 pair of the split-precision mode
+__device__ __forceinline__ void split_op16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_op16x2(a, b);
+    const float2 h = unpack_op16x2(hi);
+    lo = pack_op16x2(a - h.x, b - h.y);
+}
+
 __device__ __forceinline__ float quick_gelu(float v) {
 #ifdef MCM_GELU_EXACT
     return __fdividef(v, 1.0f + __expf(-1.702f * v));

@@ -167,7 +167,7 @@ __device__ __forceinline__ void gemm2_load_side(const GemmParams& p, int m_base,
         const int m = m_base + r0 + 4 * i;
         side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (EpiTraits<EPI>::kResid) {
-            if (m < p.m_valid && !(p.dbg_skip & 8)) side[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
+            if (m < p.m_valid && !MCM_DBG_SKIP(p, 8)) side[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
         } else {   // EPI_POS_F32: patch row m of image b carries position 1 + patch
             const int pi = m % p.np;
             if (m < p.m_valid) side[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.ldo + col));
@@ -178,14 +178,14 @@ __device__ __forceinline__ void gemm2_load_side(const GemmParams& p, int m_base,
 // t_addr: TMEM address (lane quadrant + column) of the chunk; m_base: global row of this warp's first
 // row; col0: first global column of the chunk.  s1 / s2 accumulate, per lane, the sum and the sum of
 // squares of the values written to rows r0 + 4 i (EPI_BIAS_RESID_F32_LN only).
-template <int EPI>
+template <int EPI, bool SPLIT>
 __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32_t stg, uint32_t t_addr, int m_base, int col0,
                                                      int lane, const float4 bias, const float4 (&side)[8], float (&s1)[8],
                                                      float (&s2)[8]) {
     const int cq = lane & 7;
     const int r0 = lane >> 3;
     const int col = col0 + 4 * cq;
-    if (p.dbg_skip & 4) return;
+    if (MCM_DBG_SKIP(p, 4)) return;
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_addr, acc);
     tmem_ld_wait();
@@ -200,14 +200,22 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32
         const int r = r0 + 4 * i;
         const int m = m_base + r;
         float4 v = lds_v4(stg + r * (kStgLd * 4) + ((cq ^ (r & 7)) << 4));
-        if (m < p.m_valid && (!(p.dbg_skip & 1) || v.x == 123.456f)) {
+        if (m < p.m_valid && (!MCM_DBG_SKIP(p, 1) || v.x == 123.456f)) {
             if constexpr (EpiTraits<EPI>::kResid) {
                 v.x = side[i].x + (v.x + bias.x); v.y = side[i].y + (v.y + bias.y);
                 v.z = side[i].z + (v.z + bias.z); v.w = side[i].w + (v.w + bias.w);
                 const size_t off = static_cast<size_t>(m) * p.ldo + col;
                 *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
                 if constexpr (EpiTraits<EPI>::kStats) {
-                    *reinterpret_cast<uint2*>(p.out16 + off) = make_uint2(pack_op16x2(v.x, v.y), pack_op16x2(v.z, v.w));
+                    if constexpr (SPLIT) {
+                        uint32_t h0, h1, l0, l1;
+                        split_op16x2(v.x, v.y, h0, l0);
+                        split_op16x2(v.z, v.w, h1, l1);
+                        *reinterpret_cast<uint2*>(p.out16 + off) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(p.out16_lo + off) = make_uint2(l0, l1);
+                    } else {
+                        *reinterpret_cast<uint2*>(p.out16 + off) = make_uint2(pack_op16x2(v.x, v.y), pack_op16x2(v.z, v.w));
+                    }
                     s1[i] += (v.x + v.y) + (v.z + v.w);
                     s2[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
                 }
@@ -241,9 +249,9 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // TMEM chunk (32 rows x 32 columns) -> bias / LayerNorm fold / quick_gelu -> 16 packed fp16 pairs of this thread's row.
 // release_bar != 0 (last chunk of the tile): arrive on that cluster-space tmem_empty barrier as soon as the
 // accumulator values sit in registers, so the next-but-one tile's MMAs need not wait for the math and the stores.
-template <int EPI>
+template <int EPI, bool SPLIT>
 __device__ __forceinline__ void gemm2_f16_chunk_math(const GemmParams& p, uint32_t t_addr, int col0, int lane, float rstd, float nmr,
-                                                     uint32_t release_bar, uint32_t (&pk)[16]) {
+                                                     uint32_t release_bar, uint32_t (&pk)[16], uint32_t (&pkl)[SPLIT ? 16 : 1]) {
     using T = EpiTraits<EPI>;
     static_assert(T::kF16, "fp16-output epilogues only");
     uint32_t acc[32];
@@ -282,10 +290,19 @@ __device__ __forceinline__ void gemm2_f16_chunk_math(const GemmParams& p, uint32
                 v3 = __uint_as_float(acc[a + 3]) + bias[j].w;
             }
             if constexpr (T::kGelu) {
-                v0 = quick_gelu(v0); v1 = quick_gelu(v1); v2 = quick_gelu(v2); v3 = quick_gelu(v3);
+                if constexpr (SPLIT) {
+                    v0 = quick_gelu_precise(v0); v1 = quick_gelu_precise(v1); v2 = quick_gelu_precise(v2); v3 = quick_gelu_precise(v3);
+                } else {
+                    v0 = quick_gelu(v0); v1 = quick_gelu(v1); v2 = quick_gelu(v2); v3 = quick_gelu(v3);
+                }
             }
-            pk[8 * h + 2 * j + 0] = pack_op16x2(v0, v1);
-            pk[8 * h + 2 * j + 1] = pack_op16x2(v2, v3);
+            if constexpr (SPLIT) {
+                split_op16x2(v0, v1, pk[8 * h + 2 * j + 0], pkl[8 * h + 2 * j + 0]);
+                split_op16x2(v2, v3, pk[8 * h + 2 * j + 1], pkl[8 * h + 2 * j + 1]);
+            } else {
+                pk[8 * h + 2 * j + 0] = pack_op16x2(v0, v1);
+                pk[8 * h + 2 * j + 1] = pack_op16x2(v2, v3);
+            }
         }
     }
 }
@@ -313,7 +330,7 @@ template <int EPI, int BLOCK_N>
 __device__ __forceinline__ void gemm2_epilogue_slice_f16_direct(const GemmParams& p, uint32_t t_addr, int m_base, int col0, int lane,
                                                                 float rstd, float nmr, uint32_t release_bar) {
     constexpr int kChunks = BLOCK_N / 128;   // 32-column chunks per slice
-    if (p.dbg_skip & 4) {
+    if (MCM_DBG_SKIP(p, 4)) {
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(release_bar);
@@ -323,9 +340,9 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16_direct(const GemmParams
     op16_t* orow = static_cast<op16_t*>(p.out) + static_cast<size_t>(m) * p.ldo + col0;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
-        uint32_t pk[16];
-        gemm2_f16_chunk_math<EPI>(p, t_addr + c * 32, col0 + c * 32, lane, rstd, nmr, c + 1 == kChunks ? release_bar : 0u, pk);
-        if (m < p.m_valid && !(p.dbg_skip & 1)) {
+        uint32_t pk[16], pkl[1];
+        gemm2_f16_chunk_math<EPI, false>(p, t_addr + c * 32, col0 + c * 32, lane, rstd, nmr, c + 1 == kChunks ? release_bar : 0u, pk, pkl);
+        if (m < p.m_valid && !MCM_DBG_SKIP(p, 1)) {
             stg_256(orow + c * 32, pk);
             stg_256(orow + c * 32 + 16, pk + 8);
         }
@@ -336,12 +353,12 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16_direct(const GemmParams
 // written into the warp's staging tile in the TMA swizzle layout of the output box (128-byte rows / SWIZZLE_128B
 // for 64-column slices, 64-byte rows / SWIZZLE_64B for 32-column slices -- conflict-free for a row-per-thread
 // writer) and leave as ONE bulk store per tile; rows beyond the tensor are clipped by the TMA unit.
-template <int EPI, int BLOCK_N>
+template <int EPI, int BLOCK_N, bool SPLIT>
 __device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, const CUtensorMap* tmap_out, uint32_t stg,
                                                          uint32_t t_addr, int m_base, int col0, int lane, float rstd, float nmr,
                                                          uint32_t release_bar) {
     constexpr int kChunks = BLOCK_N / 128;   // 32-column chunks per slice
-    if (p.dbg_skip & 4) {
+    if (MCM_DBG_SKIP(p, 4)) {
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(release_bar);
@@ -349,8 +366,16 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, co
     }
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
-        uint32_t pk[16];
-        gemm2_f16_chunk_math<EPI>(p, t_addr + c * 32, col0 + c * 32, lane, rstd, nmr, c + 1 == kChunks ? release_bar : 0u, pk);
+        uint32_t pk[16], pkl[SPLIT ? 16 : 1];
+        gemm2_f16_chunk_math<EPI, SPLIT>(p, t_addr + c * 32, col0 + c * 32, lane, rstd, nmr, c + 1 == kChunks ? release_bar : 0u, pk, pkl);
+        if constexpr (SPLIT) {   // low halves: two 32-byte stores of this thread's row (the k-loop is 3x longer: off the critical path)
+            const int m = m_base + lane;
+            if (m < p.m_valid) {
+                op16_t* orow = p.out_lo + static_cast<size_t>(m) * p.ldo + col0 + c * 32;
+                stg_256(orow, pkl);
+                stg_256(orow + 16, pkl + 8);
+            }
+        }
         if (c == 0) {   // the previous tile's store must have read the staging tile (issued a whole main loop ago)
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -369,7 +394,7 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, co
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0 && !(p.dbg_skip & 1)) {
+    if (lane == 0 && !MCM_DBG_SKIP(p, 1)) {
         tma_store_2d(tmap_out, stg, col0, m_base);
         tma_store_commit();
     }
@@ -391,11 +416,14 @@ __device__ __forceinline__ void tma_load_2d_plain(uint32_t smem_dst, const void*
 }
 
 // p.m_tiles counts 256-row pair tiles.  Launched with cudaLaunchKernelEx + cluster dimension 2.
-template <int BLOCK_N, int EPI>
+// SPLIT: split-fp16 precision mode (gemm_tcgen05.cuh): tmap_a_lo / tmap_b_lo are the low halves of A / W.
+template <int BLOCK_N, int EPI, bool SPLIT>
 __global__ void __launch_bounds__(EpiTraits<EPI>::kThreads, 1)
 gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out16,
+                        const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                         const GemmParams p) {
+    static_assert(!(SPLIT && EpiTraits<EPI>::kTmaResid), "the split mode uses the LSU residual epilogue");
     using L = Gemm2Smem<BLOCK_N, EPI>;
     using T = EpiTraits<EPI>;
     constexpr int kStages = L::kStages;
@@ -419,10 +447,15 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     const int num_tiles = p.m_tiles * p.n_tiles;
+    const int k_total = SPLIT ? 3 * p.k_blocks : p.k_blocks;   // SPLIT: (hi, hi), (lo, hi), (hi, lo) per k-block
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if constexpr (SPLIT) {
+            tma_prefetch_desc(&tmap_a_lo);
+            tma_prefetch_desc(&tmap_b_lo);
+        }
         if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid) tma_prefetch_desc(&tmap_out);
         if constexpr (T::kTmaResid) tma_prefetch_desc(&tmap_out16);
         for (int i = 0; i < kStages; ++i) {
@@ -455,14 +488,23 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const int n_blk = tile - m_blk * p.n_tiles;
                 const int a_row = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM;
                 const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                for (int kt = 0; kt < k_total; ++kt) {
+                    int kb = kt;
+                    const CUtensorMap* ta = &tmap_a;
+                    const CUtensorMap* tb = &tmap_b;
+                    if constexpr (SPLIT) {
+                        kb = kt / 3;
+                        const int seg = kt - 3 * kb;
+                        if (seg == 1) ta = &tmap_a_lo;
+                        if (seg == 2) tb = &tmap_b_lo;
+                    }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
                     uint8_t* sb = sa + L::kABytes;
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
                     const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                    tma_load_2d_cta2(sa, &tmap_a, bar, kb * kGemmBlockK, a_row);
-                    tma_load_2d_cta2(sb, &tmap_b, bar, kb * kGemmBlockK, b_row);
+                    tma_load_2d_cta2(sa, ta, bar, kb * kGemmBlockK, a_row);
+                    tma_load_2d_cta2(sb, tb, bar, kb * kGemmBlockK, b_row);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -485,7 +527,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 MCM_TR(t_acc, mbar_wait(&tmem_empty[as], aphase ^ 1));
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                for (int kb = 0; kb < k_total; ++kb) {
                     MCM_TR(t_full, mbar_wait(&full_bar[stage], phase));
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
@@ -562,7 +604,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const uint32_t release_bar = mapa_shared(smem_u32(&tmem_empty[as]), 0);   // the pair leader's barrier
                 if (m_base < p.m_valid) {
 #if MCM_GEMM_F16_TMA_STORE
-                    gemm2_epilogue_slice_f16<EPI, BLOCK_N>(p, &tmap_out, stg, t_row, m_base, col_base, lane, rstd, nmr, release_bar);
+                    gemm2_epilogue_slice_f16<EPI, BLOCK_N, SPLIT>(p, &tmap_out, stg, t_row, m_base, col_base, lane, rstd, nmr, release_bar);
 #else
                     gemm2_epilogue_slice_f16_direct<EPI, BLOCK_N>(p, t_row, m_base, col_base, lane, rstd, nmr, release_bar);
 #endif
@@ -729,7 +771,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
                         if constexpr (T::kResid)
                             bias = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + c * 32 + 4 * (lane & 7)));
-                        gemm2_epilogue_chunk<EPI>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias, side[c & 1], s1, s2);
+                        gemm2_epilogue_chunk<EPI, SPLIT>(p, stg, t_row + c * 32, m_base, col_base + c * 32, lane, bias, side[c & 1], s1, s2);
                     }
                 }
                 if constexpr (T::kStats) {

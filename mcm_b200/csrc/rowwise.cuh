@@ -72,7 +72,27 @@ struct WarpRow {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) d2[i * 32 + lane] = make_uint2(pack_op16x2(v[i].x, v[i].y), pack_op16x2(v[i].z, v[i].w));
     }
+    // split-precision mode: the row as an fp16 (hi, lo) pair, hi = fp16(x), lo = fp16(x - hi)
+    __device__ __forceinline__ void store_f16_split(op16_t* __restrict__ dst_hi, op16_t* __restrict__ dst_lo, int lane) const {
+        uint2* h2 = reinterpret_cast<uint2*>(dst_hi);
+        uint2* l2 = reinterpret_cast<uint2*>(dst_lo);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const uint32_t h0 = pack_op16x2(v[i].x, v[i].y), h1 = pack_op16x2(v[i].z, v[i].w);
+            const float2 a = unpack_op16x2(h0), b = unpack_op16x2(h1);
+            h2[i * 32 + lane] = make_uint2(h0, h1);
+            l2[i * 32 + lane] = make_uint2(pack_op16x2(v[i].x - a.x, v[i].y - a.y), pack_op16x2(v[i].z - b.x, v[i].w - b.y));
+        }
+    }
 };
+
+__device__ __forceinline__ float op16_to_float(op16_t q) {
+#ifdef MCM_OP_BF16
+    return __bfloat162float(q);
+#else
+    return __half2float(q);
+#endif
+}
 
 // x f32 [M, D] -> LayerNorm -> fp16 or f32 [M, D]
 template <int VEC, bool OUT_F16>
@@ -101,9 +121,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // the row (xh) and its (sum, sum of squares) as part 0 of the row statistics.
 template <int VEC>
 __global__ void __launch_bounds__(kRowThreads)
-embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, float2* __restrict__ stats, const float* __restrict__ cls,
-                    const float* __restrict__ pos, const float* __restrict__ pre_g, const float* __restrict__ pre_b, int M, int S,
-                    float eps) {
+embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, op16_t* __restrict__ xh_lo, float2* __restrict__ stats,
+                    const float* __restrict__ cls, const float* __restrict__ pos, const float* __restrict__ pre_g,
+                    const float* __restrict__ pre_b, int M, int S, float eps) {
     constexpr int D = 128 * VEC;
     pdl_launch_dependents();
     pdl_wait();
@@ -120,7 +140,10 @@ embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, float2* __re
     r.layernorm(pre_g, pre_b, eps, lane);
     r.store_f32(x + static_cast<size_t>(row) * D, lane);
     if (xh != nullptr) {
-        r.store_f16(xh + static_cast<size_t>(row) * D, lane);
+        if (xh_lo != nullptr)      // split-precision mode
+            r.store_f16_split(xh + static_cast<size_t>(row) * D, xh_lo + static_cast<size_t>(row) * D, lane);
+        else
+            r.store_f16(xh + static_cast<size_t>(row) * D, lane);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -136,32 +159,37 @@ embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, float2* __re
 // LayerNorm fold of one projection (gemm_tcgen05.cuh), one warp per output row n of W [N, K]:
 //   w16[n, k] = fp16(gamma[k] * W[n, k]),  c[n] = sum_k w16[n, k] (the ROUNDED operand, so that a constant
 //   row cancels exactly),  d[n] = bias[n] + sum_k beta[k] * W[n, k]
+// Split-precision mode (w16_lo / c_split non-null): w16_lo = fp16(gamma * W - w16), c_split[n] = sum_k (w16 + w16_lo)[n, k].
 __global__ void __launch_bounds__(256)
 fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ bias, op16_t* __restrict__ w16, float* __restrict__ c, float* __restrict__ d,
-                      int N, int K) {
+                      int N, int K, op16_t* __restrict__ w16_lo = nullptr, float* __restrict__ c_split = nullptr) {
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= N) return;
     const float* wr = w + static_cast<size_t>(n) * K;
     op16_t* o = w16 + static_cast<size_t>(n) * K;
-    float sc = 0.f, sd = 0.f;
+    float sc = 0.f, sd = 0.f, sl = 0.f;
     for (int k = lane; k < K; k += 32) {
         const float v = wr[k];
-        const op16_t q = to_op16(gamma[k] * v);
+        const float gw = gamma[k] * v;
+        const op16_t q = to_op16(gw);
         o[k] = q;
-#ifdef MCM_OP_BF16
-        sc += __bfloat162float(q);
-#else
-        sc += __half2float(q);
-#endif
+        sc += op16_to_float(q);
+        if (w16_lo != nullptr) {
+            const op16_t ql = to_op16(gw - op16_to_float(q));
+            w16_lo[static_cast<size_t>(n) * K + k] = ql;
+            sl += op16_to_float(ql);
+        }
         sd = fmaf(beta[k], v, sd);
     }
     sc = warp_sum(sc);
     sd = warp_sum(sd);
+    sl = warp_sum(sl);
     if (lane == 0) {
         c[n] = sc;
         d[n] = bias[n] + sd;
+        if (c_split != nullptr) c_split[n] = sc + sl;
     }
 }
 
@@ -173,8 +201,16 @@ fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ gam
 // (G * 3 p^2 halves, <= 43 KB) and leave as contiguous 8-byte runs (3 p^2 fp16 = 6 p^2 bytes per patch).
 __host__ __device__ inline int patchify_smem_bytes(int G, int p) { return G * 3 * p * p * 2; }
 
+// lo_pass != 0 (split-precision mode, second launch): writes fp16(v - fp16(v)), the low halves of the same values.
+__device__ __forceinline__ uint32_t patch_pack(float a, float b, int lo_pass) {
+    const uint32_t hi = pack_op16x2(a, b);
+    if (!lo_pass) return hi;
+    const float2 h = unpack_op16x2(hi);
+    return pack_op16x2(a - h.x, b - h.y);
+}
+
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp) {
+patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp, int lo_pass) {
     extern __shared__ __align__(16) uint8_t patchify_smem[];
     op16_t* tile = reinterpret_cast<op16_t*>(patchify_smem);      // [G][3 p^2]
     pdl_launch_dependents();
@@ -198,7 +234,7 @@ patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int
         for (int e = 0; e < 4; e += 2) {           // x is even and p is even: a pixel pair never straddles two patches
             const int gx = (x + e) / p;
             const int j = (x + e) - gx * p;
-            *reinterpret_cast<uint32_t*>(tile + gx * kpatch + ci * p + j) = pack_op16x2(vs[e], vs[e + 1]);
+            *reinterpret_cast<uint32_t*>(tile + gx * kpatch + ci * p + j) = patch_pack(vs[e], vs[e + 1], lo_pass);
         }
     }
     __syncthreads();
@@ -223,7 +259,8 @@ patchify_kernel(const float* __restrict__ img, op16_t* __restrict__ patches, int
 struct NormConst { float mean[3], std[3]; };
 
 __global__ void __launch_bounds__(256)
-patchify_u8_kernel(const uint8_t* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp, const NormConst nc) {
+patchify_u8_kernel(const uint8_t* __restrict__ img, op16_t* __restrict__ patches, int G, int p, int Kp, const NormConst nc,
+                   int lo_pass) {
     extern __shared__ __align__(16) uint8_t patchify_smem[];
     op16_t* tile = reinterpret_cast<op16_t*>(patchify_smem);      // [G][3 p^2]
     pdl_launch_dependents();
@@ -255,7 +292,7 @@ patchify_u8_kernel(const uint8_t* __restrict__ img, op16_t* __restrict__ patches
             const int j = (x + e) - gx * p;
             op16_t* d = tile + gx * kpatch + i * p + j;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t*>(d + c * p * p) = pack_op16x2(v[e][c], v[e + 1][c]);
+            for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t*>(d + c * p * p) = patch_pack(v[e][c], v[e + 1][c], lo_pass);
         }
     }
     __syncthreads();
@@ -269,15 +306,18 @@ patchify_u8_kernel(const uint8_t* __restrict__ img, op16_t* __restrict__ patches
     }
 }
 
-// fp32 -> fp16 with row re-striding (weight packing): dst[r * dst_ld + c] = src[r * cols + c]
-__global__ void convert_rows_f16_kernel(const float* __restrict__ src, op16_t* __restrict__ dst, int64_t rows,
-                                         int cols, int dst_ld) {
+// fp32 -> fp16 with row re-striding (weight packing): dst[r * dst_ld + c] = src[r * cols + c];
+// dst_lo (nullable): the low halves fp16(src - dst) of the split-precision mode
+__global__ void convert_rows_f16_kernel(const float* __restrict__ src, op16_t* __restrict__ dst, op16_t* __restrict__ dst_lo,
+                                         int64_t rows, int cols, int dst_ld) {
     const int64_t total = rows * cols;
     for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = t / cols;
         const int c = static_cast<int>(t - r * cols);
-        dst[r * dst_ld + c] = to_op16(src[t]);
+        const op16_t q = to_op16(src[t]);
+        dst[r * dst_ld + c] = q;
+        if (dst_lo != nullptr) dst_lo[r * dst_ld + c] = to_op16(src[t] - op16_to_float(q));
     }
 }
 

@@ -60,6 +60,7 @@ class McmEngine:
             torch.zeros(1, device=self.device)  # make sure the primary context exists
             _lib.check(self._lib.mcm_create(C.byref(self._ccfg), C.byref(self._h)), None)
         self.K = 0
+        self.precision = "fp16"
 
     # ------------------------------------------------------------------ lifecycle --
     def close(self):
@@ -430,6 +431,45 @@ class McmEngine:
 
     def reset_launch_count(self) -> None:
         self._lib.mcm_reset_launch_count(self._h)
+
+    def set_precision(self, mode) -> None:
+        """``"fp16"`` / 0 (default): one fp16 value per tensor-core operand element.  ``"split"`` / 1: fp16 (hi, lo)
+        operand pairs and three-term products -- fp32-class results (AUROC / FPR95 identical to the fp32 reference to
+        the parity bar) at 3x the tensor work.  See ``MCM_OPT_PRECISION`` in include/mcm_b200.h."""
+        if mode not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of 'fp16', 'split' (got {mode!r})")
+        self._check(self._lib.mcm_set_option(self._h, _lib.OPT_PRECISION, _lib.PRECISIONS[mode]))
+        self.precision = "split" if _lib.PRECISIONS[mode] == _lib.PRECISION_SPLIT else "fp16"
+
+    def set_cuda_graph(self, on: bool) -> None:
+        """Replay the forward from a CUDA graph captured per (input buffer, batch size, options): small batches."""
+        self._check(self._lib.mcm_set_option(self._h, _lib.OPT_CUDA_GRAPH, 1 if on else 0))
+
+    def allgather_scores(self, nccl_comm: int, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """``mcm_allgather_scores``: one NCCL all-gather of this rank's (padded) score vector on the current stream;
+        ``nccl_comm`` is a raw ``ncclComm_t`` (see :class:`mcm_b200.parallel.NcclComm`)."""
+        if local.dtype != torch.float32 or out.dtype != torch.float32 or not local.is_contiguous() or not out.is_contiguous():
+            raise ValueError("local / out must be contiguous float32 device tensors")
+        self._check(self._lib.mcm_allgather_scores(self._h, C.c_void_p(int(nccl_comm)), _ptr(local), int(local.numel()), _ptr(out),
+                                                   self._stream()))
+        return out
+
+    def dbg_gemm_split(self, a_hi, a_lo, w_hi, w_lo, bias, resid):
+        """resid + (a_hi + a_lo) @ (w_hi + w_lo)^T + bias through the three-term split GEMM (fp32 out)."""
+        M, K = a_hi.shape
+        N = w_hi.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        self._check(self._lib.mcm_dbg_gemm_split(self._h, _ptr(a_hi.contiguous()), _ptr(a_lo.contiguous()), _ptr(w_hi.contiguous()),
+                                                 _ptr(w_lo.contiguous()), _ptr(bias), _ptr(resid.contiguous()), _ptr(out), M, N, K,
+                                                 self._stream()))
+        return out
+
+    def dbg_attention_split(self, qkv_hi, qkv_lo, b: int, S: int, H: int):
+        o_hi = torch.empty((b * S, H * 64), dtype=torch.float16, device=self.device)
+        o_lo = torch.empty_like(o_hi)
+        self._check(self._lib.mcm_dbg_attention_split(self._h, _ptr(qkv_hi.contiguous()), _ptr(qkv_lo.contiguous()), _ptr(o_hi),
+                                                      _ptr(o_lo), b, S, H, self._stream()))
+        return o_hi, o_lo
 
     def set_cls_shortcut(self, on: bool) -> None:
         """Last-layer CLS-only shortcut (default on; identical results, ~6 % fewer executed FLOPs)."""

@@ -7,6 +7,9 @@ all-gather of the padded per-rank score vectors collates them (SURVEY.md section
 collective on the data path; the gather moves <= 25 KB per rank per stream.
 
 ``torch.distributed`` is the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+:class:`NcclComm` + :func:`gather_scores_nccl` are the same collation through the C ABI
+(``mcm_allgather_scores(handle, ncclComm_t, ...)``) on a raw NCCL communicator --
+the route a non-PyTorch host (the C / C++ integrator of INTEGRATION.md) takes.
 """
 from __future__ import annotations
 
@@ -16,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_len", "gather_scores", "world"]
+__all__ = ["shard_bounds", "shard_len", "gather_scores", "world", "NcclComm", "gather_scores_nccl"]
 
 
 def world() -> Tuple[int, int]:
@@ -61,4 +64,70 @@ def gather_scores(local, n: int, group=None, device: Optional[torch.device] = No
     send[: t.numel()] = t.to(device)
     recv = torch.empty((W * per,), dtype=torch.float32, device=device)
     dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:n].cpu().numpy().astype(np.float32, copy=True)
+
+
+class NcclComm:
+    """A raw ``ncclComm_t`` over the ranks of the current ``torch.distributed`` job, created with NCCL's own C API
+    (ctypes on the ``libnccl.so.2`` torch ships, i.e. the copy already mapped into the process): rank 0 makes the
+    unique id, ``torch.distributed`` (any backend) carries it to the other ranks, every rank calls
+    ``ncclCommInitRank``.  ``.handle`` is what ``mcm_allgather_scores`` takes."""
+
+    def __init__(self, device: int, group=None):
+        import ctypes as C
+        import os
+        rank, W = world()
+        self._C = C
+        path = None
+        try:
+            import nvidia.nccl as _n
+            path = os.path.join(list(_n.__path__)[0], "lib", "libnccl.so.2")
+        except Exception:
+            pass
+        self._nccl = C.CDLL(path if path and os.path.isfile(path) else "libnccl.so.2")
+        self._nccl.ncclGetErrorString.restype = C.c_char_p
+        class UniqueId(C.Structure):          # ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+            _fields_ = [("internal", C.c_byte * 128)]
+
+        uid = UniqueId()
+        if rank == 0:
+            self._nccl.ncclGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+            self._ok(self._nccl.ncclGetUniqueId(C.byref(uid)))
+        box = [bytes(uid)]
+        if W > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        uid = UniqueId.from_buffer_copy(box[0])
+        self.comm = C.c_void_p()
+        with torch.cuda.device(device):
+            self._nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+            self._nccl.ncclCommInitRank.restype = C.c_int
+            self._ok(self._nccl.ncclCommInitRank(C.byref(self.comm), W, uid, rank))
+        self.rank, self.world_size = rank, W
+
+    def _ok(self, r):
+        if r != 0:
+            raise RuntimeError("NCCL: " + self._nccl.ncclGetErrorString(r).decode())
+
+    @property
+    def handle(self) -> int:
+        return int(self.comm.value)
+
+    def close(self):
+        if getattr(self, "comm", None) is not None and self.comm.value:
+            self._nccl.ncclCommDestroy.argtypes = [self._C.c_void_p]
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = self._C.c_void_p()
+
+
+def gather_scores_nccl(engine, comm: NcclComm, local: torch.Tensor, n: int) -> np.ndarray:
+    """:func:`gather_scores` through ``mcm_allgather_scores``: ``local`` is this rank's device tensor of
+    ``shard_bounds`` scores; one ``ncclAllGather`` on the current stream; every rank gets float32 ``[n]``."""
+    lo, hi = shard_bounds(n, comm.rank, comm.world_size)
+    if local.numel() != hi - lo:
+        raise ValueError(f"rank {comm.rank} holds {local.numel()} scores, expected {hi - lo} for n={n}, world={comm.world_size}")
+    per = shard_len(n, comm.world_size)
+    send = torch.zeros((per,), dtype=torch.float32, device=engine.device)
+    send[: local.numel()] = local.to(engine.device, dtype=torch.float32).reshape(-1)
+    recv = torch.empty((comm.world_size * per,), dtype=torch.float32, device=engine.device)
+    engine.allgather_scores(comm.handle, send, recv)
     return recv[:n].cpu().numpy().astype(np.float32, copy=True)

@@ -7,8 +7,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mcm_b200 import synth  # noqa: E402
+from mcm_b200 import _lib, synth  # noqa: E402
 from mcm_b200.engine import McmEngine  # noqa: E402
+
+if os.environ.get("SWEEP_LIB"):       # A/B variant built by mcm_b200.build.build_variant
+    _lib.use_library(os.environ["SWEEP_LIB"])
 
 cfg = synth.CFGS["tiny"]
 eng = McmEngine.from_state_dict(synth.synth_vision_state_dict(cfg, 5), cfg, max_batch=4)
@@ -25,5 +28,5 @@ for b, S, H in shapes:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 20
-    print(json.dumps(dict(lib=os.environ.get("MCM_B200_LIB", "default"), mma=os.environ.get("MCM_ATTN_MMA", "0"), b=b, S=S, H=H,
+    print(json.dumps(dict(lib=os.path.basename(os.environ.get("SWEEP_LIB", "default")), b=b, S=S, H=H,
                           us=us, tflops=4.0 * b * H * S * S * 64 / us / 1e6)), flush=True)
