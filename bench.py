@@ -20,6 +20,10 @@ pre-encoded bank -> softmax/T -> max) over one batch of `--batch` synthetic 224x
   timed on this box's host cores on a bounded sample (rank 0, N = 1 only).
 * ``--impl reference``: the reference's CPU implementation of the path on the host cores
   (oracle port; /root/reference cannot travel to the GPU box), same metric / config.
+* ``verify``: every run (any N) also scores one FIXED seeded stream, sharded over the ranks with
+  ``mcm_b200.parallel.shard_bounds`` and collated with the path's one all-gather; the line carries the SHA-1 of the
+  gathered fp32 scores (identical for N = 1, 2, 4, 8) and whether it equals rank 0's own single-rank pass.
+* ``precision_split``: the same step in the split-fp16 precision mode (the mode in which FPR95 parity is exact).
 """
 from __future__ import annotations
 
@@ -133,6 +137,29 @@ def cpu_reference_rate(cfg, sd, bank, n_images, repeats=1):
     return n_images / best, best
 
 
+def cpu_as_shipped_rates(cfg, sd, K):
+    """The reference loop AS SHIPPED (utils/detection_util.py:216,228-231: tokenizer + whole text tower re-run for every
+    image batch) on the host cores: BASELINE configs[0] exactly (N = 256, B = 256, K = 10) and one batch of the bench
+    workload (B = 256, K).  The text tower is HuggingFace's, random-init at the real ViT-B/16 text shape (63 M parameters)."""
+    from mcm_b200 import synth
+    from oracle import clip_mcm_oracle as O
+    from oracle import reference_shims as R
+    from transformers import CLIPConfig, CLIPModel
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(5)
+    model = CLIPModel(CLIPConfig(projection_dim=cfg.proj)).eval()      # default text config == CLIP ViT-B text tower; only the text side is used
+    tok = R.FakeTokenizer()
+    imgs = torch.from_numpy(synth.synth_images(256, 4321))
+    out = {}
+    O.ood_scores_as_shipped(imgs[:8], sd, cfg, model, tok, ["warm", "up"], batch=8)
+    for name, labels in (("config1_n256_b256_k10", [f"class {i}" for i in range(10)]), (f"b256_k{K}", [f"class {i}" for i in range(K)])):
+        t0 = time.perf_counter()
+        O.ood_scores_as_shipped(imgs, sd, cfg, model, tok, labels, T=1, score="MCM", batch=256)
+        dt = time.perf_counter() - t0
+        out[name] = {"value": 256 / dt, "unit": UNIT, "seconds": dt}
+    return out
+
+
 def run_reference(args, rank):
     """`--impl reference`: the reference's own CPU path for the same metric/config (rank 0 only)."""
     if rank != 0:
@@ -185,8 +212,10 @@ def main():
     from mcm_b200 import synth
     from mcm_b200.engine import McmEngine
 
+    from mcm_b200 import parallel
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpus = parallel.pin_to_gpu_numa(local_rank)      # one rank per GPU: host buffers and launch thread next to that GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = synth.CFGS[args.model]
@@ -216,6 +245,7 @@ def main():
 
     # ---------------- device-resident timed region ----------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
     def timed_region():
         sampler = ClockSampler(local_rank)
@@ -226,6 +256,7 @@ def main():
         ev0.record(stream)
         for i in range(args.steps):
             step(i, scores[i * B:(i + 1) * B])
+            step_ev[i].record(stream)
         if world > 1:   # the path's one collective: collate the per-rank scores of the stream
             recv = torch.empty((world * args.steps * B,), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(recv, scores[: args.steps * B])
@@ -248,6 +279,33 @@ def main():
         if clocks is not None:
             clocks["first_attempt_rejected"] = first
     value = world * args.steps * B / (ms * 1e-3)
+    per_step = [(ev0 if i == 0 else step_ev[i - 1]).elapsed_time(step_ev[i]) for i in range(args.steps)]      # this rank's steps
+    step_ms = {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step))} if per_step else None
+
+    # ---------------- verification: one fixed seeded stream, sharded, gathered, digested ----------------
+    import hashlib
+    n_verify, slab = 4096, 256
+
+    def verify_slab(k):      # slab k of the fixed stream: the same pixels whatever the rank count
+        gk = torch.Generator(device=dev).manual_seed(77000 + k)
+        return torch.randn((slab, 3, cfg.image_size, cfg.image_size), device=dev, generator=gk)
+
+    def score_range(lo, hi):
+        parts = []
+        for k in range(lo // slab, (hi + slab - 1) // slab):
+            x = verify_slab(k)
+            a, b_ = max(lo, k * slab) - k * slab, min(hi, (k + 1) * slab) - k * slab
+            for s0 in range(a, b_, B):
+                parts.append(eng.score(x[s0:min(s0 + B, b_)], T=1.0, score="MCM").clone())
+        return torch.cat(parts) if parts else torch.empty((0,), dtype=torch.float32, device=dev)
+
+    lo, hi = parallel.shard_bounds(n_verify, rank, world)
+    gathered = parallel.gather_scores(score_range(lo, hi), n_verify, device=dev)
+    verify = None
+    if rank == 0:
+        single = score_range(0, n_verify).cpu().numpy() if world > 1 else gathered
+        verify = {"n_images": n_verify, "score_sha1": hashlib.sha1(np.ascontiguousarray(gathered).tobytes()).hexdigest(),
+                  "matches_single_rank": bool(np.array_equal(gathered, single)), "sharding": f"contiguous over {world} rank(s), one all-gather"}
 
     # ---------------- end-to-end: host buffers through the C-ABI stream entry point ----------------
     # pinned host stream: long enough that the first (un-overlapped) H2D copy of a call is amortised
@@ -303,6 +361,25 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     value_full = world * args.steps * B / (float(t2.item()) * 1e-3)
 
+    # ---------------- the same step in the split-fp16 precision mode (fp32-class results, 3x the tensor work) ----------------
+    eng.set_cls_shortcut(True)
+    eng.set_precision("split")
+    n_split = max(2, min(args.steps, 6))
+    for i in range(2):
+        step(i, scores[:B])
+    barrier()
+    ev0.record(stream)
+    for i in range(n_split):
+        step(i, scores[i * B:(i + 1) * B])
+    ev1.record(stream)
+    barrier()
+    t3 = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    value_split = world * n_split * B / (float(t3.item()) * 1e-3)
+    eng.set_precision("fp16")
+    eng.set_cls_shortcut(False)
+
     # ---------------- per-kernel durations (instrumented pass, CUDA events on the launching stream) ----------------
     # run with the full last layer so the GEMM launches execute exactly the algorithmic GEMM FLOPs
     eng.profile(True)
@@ -340,16 +417,25 @@ def main():
             cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_sample} images of the same workload ({secs:.1f} s), torch-CPU fp32 oracle "
                                   f"port of utils/detection_util.py:209-249 + HF CLIP, bank pre-encoded, {cores} threads"}
+            if args.model == "ViT-B/16":
+                try:      # the reference exactly as shipped: tokenizer + text tower re-run per image batch (:216,228-231)
+                    cpu_base["as_shipped"] = cpu_as_shipped_rates(cfg, sd, K)
+                    cpu_base["as_shipped"]["note"] = ("256 images, batch 256, HF text tower (random init, ViT-B text shape) re-encoded per "
+                                                      "batch like utils/detection_util.py:228-231; config1 = BASELINE configs[0] exactly")
+                except Exception as e:      # transformers missing: the fair line above still stands
+                    cpu_base["as_shipped"] = {"unavailable": repr(e)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "step_ms": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
             "config": {"workload": f"CLIP {args.model} image encoder + MCM scoring, K={K} prompt bank (BASELINE "
                                    f"configs[{3 if args.model == 'ViT-L/14' else 2}] shape), synthetic 224x224 fp32 stream, "
                                    f"random-init weights",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": f"resident input pool {len(pool)} x {B * 3 * 224 * 224 * 4 / 1e6:.0f} MB rotates (> 126 MB L2)",
-                       "precision": "fp16 tensor-core operands, fp32 accumulate / residual / LayerNorm / softmax / tail"},
+                       "precision": "fp16 tensor-core operands, fp32 accumulation / LayerNorm statistics / softmax / tail, residual "
+                                    "stream as an fp16 (hi, lo) pair; precision_split = every operand an fp16 pair",
+                       "cpu_affinity": (f"{len(cpus)} cores of the GPU's NUMA node" if cpus else "unpinned (topology not readable)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
                     "d2h_bytes_per_step": B * 4},
             "e2e_uint8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2,
@@ -367,6 +453,10 @@ def main():
                          "note": "kernel figures from an instrumented pass with the full last layer (executed = "
                                  "algorithmic GEMM FLOPs); step_* = value x algorithmic FLOPs/image"},
             "no_cls_shortcut": {"value": value_full, "unit": UNIT, "step_frac": (value_full / world) * flops_img / 1e12 / pk["tf_sustained"]},
+            "precision_split": {"value": value_split, "unit": UNIT, "steps": n_split,
+                                "note": "MCM_OPT_PRECISION = split: fp16 (hi, lo) operand pairs, three-term products (fp32-class scores; "
+                                        "AUROC / FPR95 identical to the fp32 oracle on the K = 1000 streams, tests/test_gpu_parity_k1000.py)"},
+            "verify": verify,
             "kernels": kernels,
             "flops_per_image": flops_img,
         }

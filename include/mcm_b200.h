@@ -188,7 +188,10 @@ enum {
     /* MCM_OPT_CUDA_GRAPH (default 0): mcm_score / mcm_image_features (and their _u8 / stream_host forms) replay a
      * CUDA graph captured per (entry point, batch size, option set) instead of ~70 individual launches:
      * for small batches, where the forward is launch-bound. */
-    MCM_OPT_CUDA_GRAPH = 3
+    MCM_OPT_CUDA_GRAPH = 3,
+    /* MCM_OPT_ATTENTION_V1 (default 0): run the round-1 attention kernel (one 4-warp softmax group per TMEM buffer)
+     * instead of the cooperative one (all eight softmax warps on one unit); same results, kept for A/B measurements. */
+    MCM_OPT_ATTENTION_V1 = 4
 };
 enum { MCM_PRECISION_FP16 = 0, MCM_PRECISION_SPLIT = 1 };
 int mcm_set_option(McmHandle* h, int32_t option, int32_t value);
@@ -249,6 +252,11 @@ int mcm_dbg_gemm_ln(McmHandle* h, const void* a_f16, const void* w16, const floa
 int mcm_dbg_gemm_resid_ln(McmHandle* h, const void* a_f16, const void* w_f16, const float* bias, const float* resid,
                           float* out, void* out16, float* stats, int32_t M, int32_t N, int32_t K, int32_t* parts,
                           void* stream);
+/* The residual epilogue the forward runs: the residual stream is an fp16 (hi, lo) pair, updated IN PLACE:
+ * (x_hi, x_lo) <- split(x_hi + x_lo + A W^T + bias), stats = float2 [*parts][M] partial (sum, sum of squares).
+ * K <= 1024 takes the TMA form of the epilogue, longer K the LSU form. */
+int mcm_dbg_gemm_resid_h2(McmHandle* h, const void* a_f16, const void* w_f16, const float* bias, void* x_hi, void* x_lo,
+                          float* stats, int32_t M, int32_t N, int32_t K, int32_t* parts, void* stream);
 /* nn.LayerNorm over the last dim (HF:359-361): x f32 [M,D] -> out fp16 (out_f16 != 0) or f32. */
 int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* gamma, const float* beta, void* out, int32_t M,
                       int32_t D, float eps, int32_t out_f16, void* stream);

@@ -20,6 +20,7 @@ PROF_KINDS = ["patchify", "gemm_patch", "embed_finish", "gemm_qkv", "attention",
 OPT_CLS_SHORTCUT = 1
 OPT_PRECISION = 2
 OPT_CUDA_GRAPH = 3
+OPT_ATTENTION_V1 = 4
 PRECISION_FP16 = 0
 PRECISION_SPLIT = 1
 PRECISIONS = {"fp16": PRECISION_FP16, "split": PRECISION_SPLIT, 0: PRECISION_FP16, 1: PRECISION_SPLIT}
@@ -75,6 +76,7 @@ SIGNATURES = {
                                   C.c_int32, _P]),
     "mcm_dbg_gemm_resid_ln": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_int32), _P]),
+    "mcm_dbg_gemm_resid_h2": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P]),
     "mcm_dbg_layernorm": (C.c_int, [_H, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
     "mcm_dbg_attention": (C.c_int, [_H, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mcm_dbg_tail": (C.c_int, [_H, _P, C.c_int32, C.c_float, C.c_int32, _P, _P, _P]),

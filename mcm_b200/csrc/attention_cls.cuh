@@ -15,10 +15,11 @@ constexpr int kClsWarps = 4;
 constexpr int kClsMaxS = 320;
 
 // qkv_lo / o_cls_lo (both null or both non-null): split-fp16 precision mode, values are hi + lo pairs.
+// xh / xl: the residual stream (an fp16 (hi, lo) pair in both modes); x_cls receives the CLS rows in fp32.
 __global__ void __launch_bounds__(kClsWarps * 32)
-attention_cls_kernel(const op16_t* __restrict__ qkv, const op16_t* __restrict__ qkv_lo, const float* __restrict__ x,
-                     op16_t* __restrict__ o_cls, op16_t* __restrict__ o_cls_lo, float* __restrict__ x_cls, int b, int S, int H,
-                     float scale) {
+attention_cls_kernel(const op16_t* __restrict__ qkv, const op16_t* __restrict__ qkv_lo, const op16_t* __restrict__ xh,
+                     const op16_t* __restrict__ xl, op16_t* __restrict__ o_cls, op16_t* __restrict__ o_cls_lo,
+                     float* __restrict__ x_cls, int b, int S, int H, float scale) {
     __shared__ float s_q[kClsWarps][64];
     __shared__ float s_p[kClsWarps][kClsMaxS];
     pdl_launch_dependents();
@@ -34,8 +35,9 @@ attention_cls_kernel(const op16_t* __restrict__ qkv, const op16_t* __restrict__ 
 
     // gather this head's 64-column slice of the CLS row of the residual stream
     {
-        const float2 v = *reinterpret_cast<const float2*>(x + static_cast<size_t>(img) * S * D + h * 64 + lane * 2);
-        *reinterpret_cast<float2*>(x_cls + static_cast<size_t>(img) * D + h * 64 + lane * 2) = v;
+        const size_t off = static_cast<size_t>(img) * S * D + h * 64 + lane * 2;
+        const float2 vh = unpack_op16x2(*reinterpret_cast<const uint32_t*>(xh + off)), vl = unpack_op16x2(*reinterpret_cast<const uint32_t*>(xl + off));
+        *reinterpret_cast<float2*>(x_cls + static_cast<size_t>(img) * D + h * 64 + lane * 2) = make_float2(vh.x + vl.x, vh.y + vl.y);
     }
     {
         float2 qf = unpack_op16x2(*reinterpret_cast<const uint32_t*>(base + lane * 2));

@@ -116,6 +116,7 @@ struct McmHandle {
     CUtensorMap tm_patches_lo, tm_xh_lo, tm_attn_lo, tm_hid_lo;
     CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
+    bool attn_v1 = true;               // MCM_OPT_ATTENTION_V1: the round-1 kernel (one softmax group per TMEM buffer)
     bool cls_shortcut = true;
 
     // uint8 ingest: Normalize constants of the reference preprocess (utils/train_eval_util.py:27-28)
@@ -395,6 +396,9 @@ struct GemmLnArgs {
     const CUtensorMap* tb_lo = nullptr;
     op16_t* out_lo = nullptr;
     op16_t* out16_lo = nullptr;
+    // EPI_BIAS_RESID_H2_LN: the residual pair read (may alias out16 / out16_lo)
+    const op16_t* resid16 = nullptr;
+    const op16_t* resid16_lo = nullptr;
 };
 
 // C[M, N] = A[M, K] W[N, K]^T with fused epilogue.  M rows valid; A's tensor map covers >= ceil(M/128)*128 rows.
@@ -427,6 +431,8 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     p.stats_out = ln.stats_out;
     p.out_lo = ln.out_lo;
     p.out16_lo = ln.out16_lo;
+    p.resid16 = ln.resid16;
+    p.resid16_lo = ln.resid16_lo;
     const bool split = ln.ta_lo != nullptr;
     if (split && !ln.tb_lo) return fail(h, MCM_EINVAL, "split GEMM needs both low-half operands");
     // Epilogue traffic that goes through TMA (fp16 outputs; the residual epilogue of EPI_BIAS_RESID_F32_LN_TMA) needs
@@ -444,7 +450,18 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
         const bool use_tma = !split && resid == out && (force >= 0 ? force != 0 : K <= 1024);
         if (use_tma) epi = EPI_BIAS_RESID_F32_LN_TMA;
     }
-    if (f16_out && MCM_GEMM_F16_TMA_STORE) {
+    if (epi == EPI_BIAS_RESID_H2_LN) {
+        if (!ln.resid16 || !ln.resid16_lo || !ln.out16 || !ln.out16_lo || !ln.stats_out)
+            return fail(h, MCM_EINVAL, "EPI_BIAS_RESID_H2_LN needs the residual pair, the output pair and the statistics buffer");
+        // short-K GEMMs (out_proj) are bound by the residual traffic: all of it through TMA; long-K ones hide the LSU epilogue
+        // behind the main loop and keep more ring stages; the split mode's k-loop is 3x longer anyway
+        if (!split && ln.resid16 == ln.out16 && ln.resid16_lo == ln.out16_lo && K <= 1024) epi = EPI_BIAS_RESID_H2_LN_TMA;
+    }
+    if (epi == EPI_BIAS_RESID_H2_LN_TMA) {
+        int rc = make_tmap_epi(h, &tout, ln.out16, M, N, false, 32);
+        if (rc) return rc;
+        if ((rc = make_tmap_epi(h, &tout16, ln.out16_lo, M, N, false, 32))) return rc;
+    } else if (f16_out && MCM_GEMM_F16_TMA_STORE) {
         int rc = make_tmap_epi(h, &tout, out, M, N, false, bn / 4);
         if (rc) return rc;
     } else if (epi == EPI_BIAS_RESID_F32_LN_TMA) {
@@ -493,6 +510,7 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
         MCM_GEMM_SPLIT_CASE(EPI_LN_F16)
         MCM_GEMM_SPLIT_CASE(EPI_LN_QGELU_F16)
         MCM_GEMM_SPLIT_CASE(EPI_BIAS_RESID_F32_LN)
+        MCM_GEMM_SPLIT_CASE(EPI_BIAS_RESID_H2_LN)
 #undef MCM_GEMM_SPLIT_CASE
         return fail(h, MCM_EINVAL, "GEMM epilogue %d has no split-precision form", epi);
     }
@@ -506,6 +524,8 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
     MCM_GEMM_CASE(EPI_LN_QGELU_F16)
     MCM_GEMM_CASE(EPI_BIAS_RESID_F32_LN)
     MCM_GEMM_CASE(EPI_BIAS_RESID_F32_LN_TMA)
+    MCM_GEMM_CASE(EPI_BIAS_RESID_H2_LN_TMA)
+    MCM_GEMM_CASE(EPI_BIAS_RESID_H2_LN)
 #undef MCM_GEMM_CASE
     return fail(h, MCM_EINVAL, "unknown GEMM epilogue %d", epi);
 }
@@ -585,6 +605,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     p.n_extra = S > 256 ? S - 256 : 0;
     p.units_per_item = ((S < 256 ? S : 256) + 127) / 128;   // query rows >= 256 go to the tail-row warp
     p.scale_log2e = 0.125f * 1.4426950408889634f;  // dh^-0.5 (HF:292) * log2(e)
+    p.inv_H = 1.0f / static_cast<float>(H);
     p.out = out;
     p.trace = nullptr;
 #ifdef MCM_ATC_TRACE
@@ -593,12 +614,18 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     cudaMemsetAsync(trace_dev, 0, 3 * 16 * 8 * sizeof(long long), st);
     p.trace = trace_dev;
 #endif
-    const int smem = atc_smem_bytes(p.keys_pad);
-    MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_tcgen05_kernel), smem));
     const int items = p.pair_mode ? (b * H + 1) / 2 : b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
+    if (h->attn_v1) {
+        const int smem = atc_smem_bytes(p.keys_pad);
+        MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_tcgen05_kernel), smem));
+        MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
+    } else {
+        const int smem = atc_coop_smem_bytes(p.keys_pad);
+        MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_coop_kernel), smem));
+        MCM_CUDA(h, launch_k(attention_coop_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
+    }
 #ifdef MCM_ATC_TRACE
     {
         static int dumped = 0;
@@ -622,11 +649,12 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     return MCM_OK;
 }
 
-int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T, int kind, float* feats, float* scores,
-                cudaStream_t st) {
+// pooled rows: fp32 `x` (x != nullptr) or the residual pair (xh, xl)
+int launch_tail(McmHandle* h, const float* x, const op16_t* xh, const op16_t* xl, size_t row_stride, int b, float T, int kind,
+                float* feats, float* scores, cudaStream_t st) {
     if (b <= 0) return MCM_OK;
     ProfScope prof(h, MCM_PROF_TAIL, st);
-    MCM_CUDA(h, launch_k(pooled_layernorm_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, x, row_stride, h->D, b, h->post_g,
+    MCM_CUDA(h, launch_k(pooled_layernorm_kernel, dim3((b + 7) / 8), dim3(256), 0, st, 1, x, xh, xl, row_stride, h->D, b, h->post_g,
                          h->post_b, h->cfg.eps, h->t_ln));
     float* f = feats ? feats : h->t_feat;
     dim3 g1((h->P + kSgemmTile - 1) / kSgemmTile, (b + kSgemmTile - 1) / kSgemmTile);
@@ -643,7 +671,7 @@ int launch_tail(McmHandle* h, const float* x, size_t row_stride, int b, float T,
 }
 
 // images: fp32 NCHW already normalised (u8 == false) or uint8 NHWC straight from the decoder (u8 == true)
-int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st) {
+int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st, bool write_x = false) {
     const bool split = h->precision == MCM_PRECISION_SPLIT;
     {
         ProfScope prof(h, MCM_PROF_PATCHIFY, st);
@@ -672,8 +700,8 @@ int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t 
     ProfScope prof(h, MCM_PROF_EMBED_FINISH, st);
     rc = dispatch_vec(h, h->D, [&](auto vec) {
         constexpr int V = decltype(vec)::value;
-        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xh, split ? h->xh_lo : nullptr,
-                                   h->stats, h->cls, h->pos, h->pre_g, h->pre_b, M, h->S, h->cfg.eps));
+        return cuda_rc(h, launch_k(embed_finish_kernel<V>, dim3(grid), dim3(kRowThreads), 0, st, 1, h->x, h->xh, h->xh_lo,
+                                   h->stats, h->cls, h->pos, h->pre_g, h->pre_b, M, h->S, h->cfg.eps, write_x ? 1 : 0));
     });
     if (rc) return rc;
     MCM_CUDA(h, cudaGetLastError());
@@ -683,18 +711,31 @@ int launch_embed(McmHandle* h, const void* images, bool u8, int b, cudaStream_t 
 
 // embeddings + encoder.  Returns in *pooled / *pooled_stride where the rows the tail pools live:
 // the CLS rows of h->x (stride S * D) or, with the last-layer shortcut, the compact h->x_cls (stride D).
-int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st, const float** pooled, size_t* pooled_stride) {
+// where the tail finds the rows it pools: fp32 rows (x != nullptr) or the residual pair (xh, xl)
+struct PooledRows {
+    const float* x = nullptr;
+    const op16_t *xh = nullptr, *xl = nullptr;
+    size_t stride = 0;
+};
+
+// embeddings + encoder.  The residual stream lives as an fp16 (hi, lo) pair in xh / xh_lo (gemm_tcgen05.cuh,
+// EPI_BIAS_RESID_H2_*): hi is the A operand of the next projection, hi + lo carries ~22 significant bits.
+// Returns where the rows the tail pools live: the CLS rows of the pair (stride S * D) or, with the last-layer
+// shortcut, the compact fp32 h->x_cls (stride D).
+int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t st, PooledRows* pooled) {
     int rc = launch_embed(h, images, u8, b, st);
     if (rc) return rc;
     const int M = b * h->S, D = h->D, F = h->F;
     const bool split = h->precision == MCM_PRECISION_SPLIT;
-    *pooled = h->x;
-    *pooled_stride = static_cast<size_t>(h->S) * D;
+    pooled->x = nullptr;
+    pooled->xh = h->xh;
+    pooled->xl = h->xh_lo;
+    pooled->stride = static_cast<size_t>(h->S) * D;
     const int ld = static_cast<int>(h->m_pad);
     for (int i = 0; i < h->L; ++i) {
         const LayerWeights& w = h->layers[i];
         const bool last = i + 1 == h->L;
-        // consumer side of the LayerNorm fold: xh holds the raw fp16 rows of x, stats their partial sums
+        // consumer side of the LayerNorm fold: xh holds the raw fp16 rows of the residual, stats their partial sums
         // (one part after embed_finish, one per 128-column half tile after an out_proj / fc2 epilogue)
         GemmLnArgs ln1, ln2, prod, out_a, fc2_a;
         ln1.colsum = split ? w.cqkv_s : w.cqkv;
@@ -705,13 +746,16 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
         ln2 = ln1;
         ln2.colsum = split ? w.c1_s : w.c1;
         ln2.stats_parts = h->stats_parts;
+        // producer side: the residual pair is updated in place, the row statistics are a by-product
+        prod.resid16 = h->xh;
+        prod.resid16_lo = h->xh_lo;
         prod.out16 = h->xh;
+        prod.out16_lo = h->xh_lo;
         prod.stats_out = h->stats;
         prod.stats_ld = ld;
         if (split) {     // every operand is an fp16 (hi, lo) pair (gemm_tcgen05.cuh, "Precision modes")
             ln1.ta_lo = &h->tm_xh_lo;   ln1.tb_lo = &w.tm_wqkv_lo;  ln1.out_lo = h->qkv_lo;
             ln2.ta_lo = &h->tm_xh_lo;   ln2.tb_lo = &w.tm_w1_lo;    ln2.out_lo = h->hid_lo;
-            prod.out16_lo = h->xh_lo;
         }
         out_a = prod;
         fc2_a = prod;
@@ -721,23 +765,30 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
         }
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_QKV, h->tm_xh, w.tm_wqkv, M, 3 * D, D, EPI_LN_F16, w.dqkv, h->qkv, nullptr, nullptr, 0, 0, st, ln1))) return rc;
         if (last && h->cls_shortcut) {
-            // only query row 0 of every image is consumed after this point (HF:685); the b CLS rows move to
-            // x_cls, and xh / stats (free once the QKV projection has run) carry their fp16 copy and statistics
+            // only query row 0 of every image is consumed after this point (HF:685); the b CLS rows move to the fp32
+            // x_cls, and rows 0 .. b-1 of xh (/ xh_lo) and of stats (free once the QKV projection has run) carry their
+            // fp16 copy and statistics
             {
                 ProfScope prof(h, MCM_PROF_ATTENTION, st);
                 MCM_CUDA(h, launch_k(attention_cls_kernel, dim3((b * h->H + kClsWarps - 1) / kClsWarps), dim3(kClsWarps * 32), 0,
-                                     st, 1, h->qkv, split ? h->qkv_lo : nullptr, h->x, h->attn, split ? h->attn_lo : nullptr, h->x_cls, b,
-                                     h->S, h->H, 0.125f));
+                                     st, 1, h->qkv, split ? h->qkv_lo : nullptr, h->xh, h->xh_lo, h->attn, split ? h->attn_lo : nullptr,
+                                     h->x_cls, b, h->S, h->H, 0.125f));
             }
             h->launches++;
-            GemmLnArgs fc2_last;             // plain residual epilogue: no fp16 copy, no statistics
-            fc2_last.ta_lo = fc2_a.ta_lo;
-            fc2_last.tb_lo = fc2_a.tb_lo;
-            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st, out_a))) return rc;
+            GemmLnArgs out_c, fc2_c;         // b rows: fp32 residual rows, fp16 copy (+ low half in the split mode) for fc1
+            out_c.out16 = h->xh;
+            out_c.out16_lo = split ? h->xh_lo : nullptr;
+            out_c.stats_out = h->stats;
+            out_c.stats_ld = ld;
+            out_c.ta_lo = out_a.ta_lo;
+            out_c.tb_lo = out_a.tb_lo;
+            fc2_c.ta_lo = fc2_a.ta_lo;       // plain residual epilogue: no fp16 copy, no statistics
+            fc2_c.tb_lo = fc2_a.tb_lo;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, b, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x_cls, h->x_cls, nullptr, 0, 0, st, out_c))) return rc;
             if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, b, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
-            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, b, D, F, EPI_BIAS_RESID_F32, w.b2, h->x_cls, h->x_cls, nullptr, 0, 0, st, fc2_last))) return rc;
-            *pooled = h->x_cls;
-            *pooled_stride = D;
+            if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, b, D, F, EPI_BIAS_RESID_F32, w.b2, h->x_cls, h->x_cls, nullptr, 0, 0, st, fc2_c))) return rc;
+            pooled->x = h->x_cls;
+            pooled->stride = D;
             break;
         }
         if (split) {
@@ -745,14 +796,9 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
         } else {
             if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->tm_qkv_x, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
         }
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_F32_LN, w.bo, h->x, h->x, nullptr, 0, 0, st, out_a))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_H2_LN, w.bo, nullptr, nullptr, nullptr, 0, 0, st, out_a))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, M, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
-        // the last layer's output only feeds the pooled post-LN of the tail: no fp16 copy, no statistics
-        GemmLnArgs fc2_last;
-        fc2_last.ta_lo = fc2_a.ta_lo;
-        fc2_last.tb_lo = fc2_a.tb_lo;
-        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, last ? EPI_BIAS_RESID_F32 : EPI_BIAS_RESID_F32_LN, w.b2,
-                              h->x, h->x, nullptr, 0, 0, st, last ? fc2_last : fc2_a))) return rc;
+        if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC2, h->tm_hid, w.tm_w2, M, D, F, EPI_BIAS_RESID_H2_LN, w.b2, nullptr, nullptr, nullptr, 0, 0, st, fc2_a))) return rc;
     }
     return MCM_OK;
 }
@@ -992,6 +1038,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(dev_alloc(h, &h->patches, (size_t)h->mp_pad * h->Kp, true));
     MCM_TRY(dev_alloc(h, &h->x, (size_t)h->m_pad * D, true));
     MCM_TRY(dev_alloc(h, &h->xh, (size_t)h->m_pad * D, true));
+    MCM_TRY(dev_alloc(h, &h->xh_lo, (size_t)h->m_pad * D, true));      // the residual stream is the pair (xh, xh_lo)
     h->stats_parts = 2 * (D / gemm_block_n(D));   // one partial per half tile of a GEMM with N = D
     MCM_TRY(dev_alloc(h, &h->stats, (size_t)h->stats_parts * h->m_pad, true));
     MCM_TRY(dev_alloc(h, &h->qkv, (size_t)h->m_pad * 3 * D, true));
@@ -1002,6 +1049,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
     MCM_TRY(dev_alloc(h, &h->t_feat, (size_t)cfg->max_batch * h->P, false));
     MCM_TRY(make_tmap(h, &h->tm_patches, h->patches, h->mp_pad, h->Kp, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_xh, h->xh, h->m_pad, D, kGemmBlockM));
+    MCM_TRY(make_tmap(h, &h->tm_xh_lo, h->xh_lo, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_attn, h->attn, h->m_pad, D, kGemmBlockM));
     MCM_TRY(make_tmap(h, &h->tm_hid, h->hid, h->m_pad, F, kGemmBlockM));
     {
@@ -1154,13 +1202,12 @@ enum FwdMode { FWD_FEATURES = 0, FWD_SCORE = 1, FWD_MAHA = 2 };
 // the launches of one forward; `feats` / `scores` are where the tail writes
 int enqueue_forward(McmHandle* h, const void* images, bool u8, int b, int mode, float T, int kind, float* feats, float* scores,
                     cudaStream_t st) {
-    const float* pooled = nullptr;
-    size_t stride = 0;
-    int rc = forward_tower(h, images, u8, b, st, &pooled, &stride);
+    PooledRows pr;
+    int rc = forward_tower(h, images, u8, b, st, &pr);
     if (rc) return rc;
-    if (mode == FWD_FEATURES) return launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, feats, nullptr, st);
-    if (mode == FWD_SCORE) return launch_tail(h, pooled, stride, b, T, kind, nullptr, scores, st);
-    if ((rc = launch_tail(h, pooled, stride, b, 1.0f, SCORE_MCM, h->t_feat, nullptr, st))) return rc;
+    if (mode == FWD_FEATURES) return launch_tail(h, pr.x, pr.xh, pr.xl, pr.stride, b, 1.0f, SCORE_MCM, feats, nullptr, st);
+    if (mode == FWD_SCORE) return launch_tail(h, pr.x, pr.xh, pr.xl, pr.stride, b, T, kind, nullptr, scores, st);
+    if ((rc = launch_tail(h, pr.x, pr.xh, pr.xl, pr.stride, b, 1.0f, SCORE_MCM, h->t_feat, nullptr, st))) return rc;
     return launch_maha(h, h->t_feat, b, scores, st);
 }
 
@@ -1513,6 +1560,7 @@ int mcm_set_option(McmHandle* h, int32_t option, int32_t value) {
     switch (option) {
         case MCM_OPT_CLS_SHORTCUT: h->cls_shortcut = value != 0; return MCM_OK;
         case MCM_OPT_CUDA_GRAPH: h->use_graph = value != 0; return MCM_OK;
+        case MCM_OPT_ATTENTION_V1: h->attn_v1 = value != 0; return MCM_OK;
         case MCM_OPT_PRECISION: {
             if (value != MCM_PRECISION_FP16 && value != MCM_PRECISION_SPLIT) return fail(h, MCM_EINVAL, "unknown precision mode %d", value);
             if (value == MCM_PRECISION_SPLIT && !h->hid_lo) {
@@ -1522,11 +1570,9 @@ int mcm_set_option(McmHandle* h, int32_t option, int32_t value) {
                 const int D = h->D;
                 int rc;
                 if ((rc = dev_alloc(h, &h->patches_lo, (size_t)h->mp_pad * h->Kp, true))) return rc;
-                if ((rc = dev_alloc(h, &h->xh_lo, (size_t)h->m_pad * D, true))) return rc;
                 if ((rc = dev_alloc(h, &h->qkv_lo, (size_t)h->m_pad * 3 * D, true))) return rc;
                 if ((rc = dev_alloc(h, &h->attn_lo, (size_t)h->m_pad * D, true))) return rc;
                 if ((rc = make_tmap(h, &h->tm_patches_lo, h->patches_lo, h->mp_pad, h->Kp, kGemmBlockM))) return rc;
-                if ((rc = make_tmap(h, &h->tm_xh_lo, h->xh_lo, h->m_pad, D, kGemmBlockM))) return rc;
                 if ((rc = make_tmap(h, &h->tm_attn_lo, h->attn_lo, h->m_pad, D, kGemmBlockM))) return rc;
                 op16_t* hl = nullptr;
                 if ((rc = dev_alloc(h, &hl, (size_t)h->m_pad * h->F, true))) return rc;
@@ -1686,6 +1732,26 @@ int mcm_dbg_gemm_resid_ln(McmHandle* h, const void* a, const void* w, const floa
                        static_cast<cudaStream_t>(stream), ln);
 }
 
+int mcm_dbg_gemm_resid_h2(McmHandle* h, const void* a, const void* w, const float* bias, void* x_hi, void* x_lo, float* stats,
+                          int32_t M, int32_t N, int32_t K, int32_t* parts, void* stream) {
+    if (!h || !a || !w || !bias || !x_hi || !x_lo || !stats || !parts) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_resid_h2: NULL argument");
+    if (M <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_gemm_resid_h2: M must be positive");
+    if (N % 128 != 0 || K % 64 != 0) return fail(h, MCM_EUNSUPPORTED, "mcm_dbg_gemm_resid_h2: N %% 128 and K %% 64 must be 0");
+    DeviceGuard guard(h->cfg.device);
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap(h, &ta, a, M, K, kGemmBlockM))) return rc;
+    if ((rc = make_tmap(h, &tb, w, N, K, gemm_block_n(N) / 2))) return rc;
+    *parts = 2 * (N / gemm_block_n(N));
+    GemmLnArgs ln;
+    ln.resid16 = ln.out16 = static_cast<op16_t*>(x_hi);
+    ln.resid16_lo = ln.out16_lo = static_cast<op16_t*>(x_lo);
+    ln.stats_out = reinterpret_cast<float2*>(stats);
+    ln.stats_ld = M;
+    return launch_gemm(h, MCM_PROF_GEMM_OTHER, ta, tb, M, N, K, EPI_BIAS_RESID_H2_LN, bias, nullptr, nullptr, nullptr, 0, 0,
+                       static_cast<cudaStream_t>(stream), ln);
+}
+
 int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float* b, void* out, int32_t M, int32_t D,
                       float eps, int32_t out_f16, void* stream) {
     if (!h || !x || !g || !b || !out) return fail(h, MCM_EINVAL, "mcm_dbg_layernorm: NULL argument");
@@ -1710,7 +1776,7 @@ int mcm_dbg_tail(McmHandle* h, const float* x, int32_t b, float T, int32_t kind,
     int rc = check_ready(h, b, scores != nullptr);
     if (rc) return rc;
     if (!x) return fail(h, MCM_EINVAL, "mcm_dbg_tail: NULL argument");
-    return launch_tail(h, x, static_cast<size_t>(h->S) * h->D, b, T, kind, feats, scores, static_cast<cudaStream_t>(stream));
+    return launch_tail(h, x, nullptr, nullptr, static_cast<size_t>(h->S) * h->D, b, T, kind, feats, scores, static_cast<cudaStream_t>(stream));
 }
 
 int mcm_dbg_embed(McmHandle* h, const float* images, int32_t b, float* x, void* stream) {
@@ -1719,7 +1785,7 @@ int mcm_dbg_embed(McmHandle* h, const float* images, int32_t b, float* x, void* 
     if (!images || !x) return fail(h, MCM_EINVAL, "mcm_dbg_embed: NULL argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // run only pre_layrnorm here: the fused LN1 output goes to the workspace, x is copied out
-    if ((rc = launch_embed(h, images, false, b, st))) return rc;
+    if ((rc = launch_embed(h, images, false, b, st, /*write_x=*/true))) return rc;
     MCM_CUDA(h, cudaMemcpyAsync(x, h->x, (size_t)b * h->S * h->D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return MCM_OK;
 }

@@ -28,7 +28,12 @@ enum GemmEpilogue : int {
     EPI_LN_QGELU_F16 = 5,      // out_f16 = quick_gelu(the same)                      (layer_norm2 folded into fc1)
     EPI_BIAS_RESID_F32_LN = 6, // EPI_BIAS_RESID_F32 + fp16 copy of the result + partial row statistics
     EPI_BIAS_RESID_F32_LN_TMA = 7,   // the same through TMA loads / stores (the tensor maps carry resid == out and out16)
-    EPI_KINDS = 8,
+    // The residual stream of the forward is an fp16 PAIR, x = hi + lo (hi = fp16(x), lo = fp16(x - hi); ~22 significant bits):
+    // hi is the A operand the next projection reads anyway, so the pair costs 4 bytes per element where fp32 + fp16 copy
+    // cost 6, and a residual epilogue moves 8 bytes per element (read pair, write pair) instead of 10.
+    EPI_BIAS_RESID_H2_LN_TMA = 8,    // (hi, lo) = split(resid_hi + resid_lo + acc + bias) + partial row statistics, through TMA
+    EPI_BIAS_RESID_H2_LN = 9,        // the same through the LSU (long-K GEMMs, the split-precision mode)
+    EPI_KINDS = 10,
 };
 
 struct GemmParams {
@@ -40,6 +45,8 @@ struct GemmParams {
     const float* bias;  // [N] (unused for EPI_POS_F32); the folded d vector for EPI_LN_*
     void* out;          // fp16 or fp32
     const float* resid; // EPI_BIAS_RESID_F32*
+    const op16_t* resid16;     // EPI_BIAS_RESID_H2_*: residual pair (may alias out16 / out16_lo)
+    const op16_t* resid16_lo;
     const float* pos;   // EPI_POS_F32: position embedding [S, N]
     int np;             // EPI_POS_F32: patches per image
     int seq;            // EPI_POS_F32: tokens per image (np + 1)
@@ -50,11 +57,11 @@ struct GemmParams {
     int stats_ld;            // rows per part of stats_in / stats_out
     float inv_k;             // 1 / (row length the statistics were taken over)
     float eps;
-    op16_t* out16;           // EPI_BIAS_RESID_F32_LN: fp16 copy of out (the next projection's A operand)
+    op16_t* out16;           // EPI_BIAS_RESID_F32_LN: fp16 copy of out (the next projection's A operand); EPI_BIAS_RESID_H2_*: hi
     float2* stats_out;       // EPI_BIAS_RESID_F32_LN: [2 * n_tiles][stats_ld]
     // ---- split-fp16 precision mode (SPLIT kernels only; see "Precision modes" below) ----
     op16_t* out_lo;          // fp16-output epilogues: low half of out  (out + out_lo carry ~22 significant bits)
-    op16_t* out16_lo;        // EPI_BIAS_RESID_F32_LN: low half of out16
+    op16_t* out16_lo;        // EPI_BIAS_RESID_F32_LN (split mode): low half of out16; EPI_BIAS_RESID_H2_*: lo
     long long* trace;        // -DMCM_GEMM_TRACE builds: [8] cycle counters summed over CTAs (see tools/gemm_trace.py)
 #ifdef MCM_DEBUG
     int dbg_skip;            // timing experiments only (env MCM_GEMM_DBG_SKIP, -DMCM_DEBUG builds): 1 no global stores,

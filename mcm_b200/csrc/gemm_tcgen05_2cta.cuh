@@ -40,6 +40,7 @@ constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
 #endif
 constexpr int kResidBufs = MCM_RESID_BUFS;   // TMA residual epilogue: residual chunks in flight per warp
 constexpr int kResidWarpBytes = kResidBufs * 4096 + 2048;   // + the fp16 staging tile
+constexpr int kResidH2Bufs = 3;      // (hi, lo) TMA residual epilogue: 2 KB + 2 KB chunks in flight per warp (two loads ahead)
 constexpr int kMaxStatsParts = 8;    // LayerNorm fold: partial row statistics per row (width <= 1024: 2 per 256-column tile)
 constexpr int kStgLd = 32;           // fp32 staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
 
@@ -53,9 +54,11 @@ struct EpiTraits {
     static constexpr bool kLn = (EPI == EPI_LN_F16 || EPI == EPI_LN_QGELU_F16);
     static constexpr bool kGelu = (EPI == EPI_BIAS_QGELU_F16 || EPI == EPI_LN_QGELU_F16);
     static constexpr bool kF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_QGELU_F16 || kLn);
-    static constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_F32_LN);
+    static constexpr bool kResidH2 = (EPI == EPI_BIAS_RESID_H2_LN);          // residual stream as an fp16 (hi, lo) pair, LSU
+    static constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_F32_LN || kResidH2);
     static constexpr bool kTmaResid = (EPI == EPI_BIAS_RESID_F32_LN_TMA);   // residual epilogue through TMA loads / stores
-    static constexpr bool kStats = (EPI == EPI_BIAS_RESID_F32_LN);
+    static constexpr bool kTmaResidH2 = (EPI == EPI_BIAS_RESID_H2_LN_TMA);  // the (hi, lo) pair through TMA loads / stores
+    static constexpr bool kStats = (EPI == EPI_BIAS_RESID_F32_LN || kResidH2);
     static constexpr int kWarps = kF16 ? 16 : 8;
     static constexpr int kThreads = 64 + 32 * kWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 };
@@ -72,14 +75,16 @@ struct Gemm2Smem {
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagingBytes = T::kF16 ? (MCM_GEMM_F16_TMA_STORE ? 16 * (BLOCK_N / 4) * 64 : 0) : T::kTmaResid ? 8 * kResidWarpBytes : 32 * 1024;
+    static constexpr int kStagingBytes = T::kF16 ? (MCM_GEMM_F16_TMA_STORE ? 16 * (BLOCK_N / 4) * 64 : 0)
+                                         : T::kTmaResid ? 8 * kResidWarpBytes
+                                         : T::kTmaResidH2 ? 8 * kResidH2Bufs * 4096 : 32 * 1024;
     static constexpr int kBarrierBytes = 512;
     static constexpr int kBudget = 232448 - 1024 /* alignment slack */ - kBarrierBytes - kStagingBytes;
     static constexpr int kStages = (kBudget / kStageBytes) < 8 ? (kBudget / kStageBytes) : 8;
     static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
     static_assert(kStages >= 3, "too few operand stages");
     static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
-    static_assert((2 * kStages + 4 + 16) * 8 + 4 <= kBarrierBytes, "barrier area too small");
+    static_assert((2 * kStages + 5 + 8 * (kResidBufs > kResidH2Bufs ? kResidBufs : kResidH2Bufs)) * 8 + 8 <= kBarrierBytes, "barrier area too small");
 };
 
 // ---- cluster / 2-CTA PTX ----
@@ -166,7 +171,15 @@ __device__ __forceinline__ void gemm2_load_side(const GemmParams& p, int m_base,
     for (int i = 0; i < 8; ++i) {
         const int m = m_base + r0 + 4 * i;
         side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (EpiTraits<EPI>::kResid) {
+        if constexpr (EpiTraits<EPI>::kResidH2) {
+            if (m < p.m_valid) {
+                const size_t off = static_cast<size_t>(m) * p.ldo + col;
+                // RAW bits only: converting here would wait for the loads at the point of the prefetch (measured: the
+                // epilogue then stalls a full HBM round trip per chunk); gemm2_epilogue_chunk decodes them a chunk later
+                const uint2 hh = *reinterpret_cast<const uint2*>(p.resid16 + off), ll = *reinterpret_cast<const uint2*>(p.resid16_lo + off);
+                side[i] = make_float4(__uint_as_float(hh.x), __uint_as_float(hh.y), __uint_as_float(ll.x), __uint_as_float(ll.y));
+            }
+        } else if constexpr (EpiTraits<EPI>::kResid) {
             if (m < p.m_valid && !MCM_DBG_SKIP(p, 8)) side[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + col);
         } else {   // EPI_POS_F32: patch row m of image b carries position 1 + patch
             const int pi = m % p.np;
@@ -202,12 +215,18 @@ __device__ __forceinline__ void gemm2_epilogue_chunk(const GemmParams& p, uint32
         float4 v = lds_v4(stg + r * (kStgLd * 4) + ((cq ^ (r & 7)) << 4));
         if (m < p.m_valid && (!MCM_DBG_SKIP(p, 1) || v.x == 123.456f)) {
             if constexpr (EpiTraits<EPI>::kResid) {
-                v.x = side[i].x + (v.x + bias.x); v.y = side[i].y + (v.y + bias.y);
-                v.z = side[i].z + (v.z + bias.z); v.w = side[i].w + (v.w + bias.w);
+                float4 sd = side[i];
+                if constexpr (EpiTraits<EPI>::kResidH2) {     // (hi pair 0, hi pair 1, lo pair 0, lo pair 1) raw bits -> hi + lo, exact in fp32
+                    const float2 h0 = unpack_op16x2(__float_as_uint(sd.x)), h1 = unpack_op16x2(__float_as_uint(sd.y));
+                    const float2 l0 = unpack_op16x2(__float_as_uint(sd.z)), l1 = unpack_op16x2(__float_as_uint(sd.w));
+                    sd = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+                }
+                v.x = sd.x + (v.x + bias.x); v.y = sd.y + (v.y + bias.y);
+                v.z = sd.z + (v.z + bias.z); v.w = sd.w + (v.w + bias.w);
                 const size_t off = static_cast<size_t>(m) * p.ldo + col;
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
+                if constexpr (!EpiTraits<EPI>::kResidH2) *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
                 if constexpr (EpiTraits<EPI>::kStats) {
-                    if constexpr (SPLIT) {
+                    if constexpr (SPLIT || EpiTraits<EPI>::kResidH2) {
                         uint32_t h0, h1, l0, l1;
                         split_op16x2(v.x, v.y, h0, l0);
                         split_op16x2(v.z, v.w, h1, l1);
@@ -423,7 +442,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out16,
                         const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                         const GemmParams p) {
-    static_assert(!(SPLIT && EpiTraits<EPI>::kTmaResid), "the split mode uses the LSU residual epilogue");
+    static_assert(!(SPLIT && (EpiTraits<EPI>::kTmaResid || EpiTraits<EPI>::kTmaResidH2)), "the split mode uses the LSU residual epilogues");
     using L = Gemm2Smem<BLOCK_N, EPI>;
     using T = EpiTraits<EPI>;
     constexpr int kStages = L::kStages;
@@ -456,8 +475,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             tma_prefetch_desc(&tmap_a_lo);
             tma_prefetch_desc(&tmap_b_lo);
         }
-        if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid) tma_prefetch_desc(&tmap_out);
-        if constexpr (T::kTmaResid) tma_prefetch_desc(&tmap_out16);
+        if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid || T::kTmaResidH2) tma_prefetch_desc(&tmap_out);
+        if constexpr (T::kTmaResid || T::kTmaResidH2) tma_prefetch_desc(&tmap_out16);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -468,6 +487,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
         if constexpr (T::kTmaResid)
             for (int i = 0; i < 8 * kResidBufs; ++i) mbar_init(&tmem_ptr_bars[i], 1);
+        if constexpr (T::kTmaResidH2)
+            for (int i = 0; i < 8 * kResidH2Bufs; ++i) mbar_init(&tmem_ptr_bars[i], 1);
         fence_barrier_init();
     }
     pdl_launch_dependents();
@@ -726,6 +747,96 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + 5), (unsigned long long)(clock64() - tb0));
 #endif
             }
+        } else if constexpr (T::kTmaResidH2) {
+            // ---- residual pair through TMA: per warp and 32 x 32 chunk the (hi, lo) fp16 tiles of the residual arrive by TMA
+            // (SWIZZLE_64B, 2 KB each, loads run kResidH2Bufs - 1 chunks ahead, across tiles); each thread owns one row: it adds
+            // its accumulator row + bias, re-splits the sum IN PLACE, accumulates the row's sum / sum of squares, and two bulk
+            // stores write the pair back.  tmap_out is the hi array (the next projection's A operand), tmap_out16 the lo array.
+            const int half = ew >> 2;               // which half of the tile's columns this warp drains
+            constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp and tile
+            const uint32_t wbase = smem_u32(staging + ew * (kResidH2Bufs * 4096));   // [kResidH2Bufs][hi 2 KB | lo 2 KB]
+            uint64_t* rbar = tmem_ptr_bars + ew * kResidH2Bufs;
+            const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+            const int n_chunks = my_tiles * kChunks;
+            auto chunk_pos = [&](int g, int& m0, int& c0) {
+                const int tile = cluster_id + (g / kChunks) * num_clusters;
+                const int m_blk = tile / p.n_tiles;
+                const int n_blk = tile - m_blk * p.n_tiles;
+                m0 = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
+                c0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + (g % kChunks) * 32;
+            };
+            auto issue_load = [&](int g) {   // lane 0 only
+                int m0, c0;
+                chunk_pos(g, m0, c0);
+                const uint32_t bar = smem_u32(&rbar[g % kResidH2Bufs]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4096) : "memory");
+                tma_load_2d_plain(wbase + (g % kResidH2Bufs) * 4096, &tmap_out, bar, c0, m0);
+                tma_load_2d_plain(wbase + (g % kResidH2Bufs) * 4096 + 2048, &tmap_out16, bar, c0, m0);
+            };
+            if (lane == 0)
+                for (int g = 0; g < kResidH2Bufs - 1 && g < n_chunks; ++g) issue_load(g);
+            float s1 = 0.f, s2 = 0.f;
+            for (int g = 0; g < n_chunks; ++g) {
+                const int c = g % kChunks;
+                int m_base, col0;
+                chunk_pos(g, m_base, col0);
+                if (c == 0) {
+                    mbar_wait(&tmem_full[as], aphase);
+                    tcgen05_fence_after();
+                }
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2) + c * 32, acc);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform: broadcast loads
+                // every bulk store committed so far has read its smem source: the buffer of chunk g - 1 is free;
+                // start the load that runs kResidH2Bufs - 1 chunks ahead into it
+                if (lane == 0) {
+                    tma_store_wait_read();
+                    if (g + kResidH2Bufs - 1 < n_chunks) issue_load(g + kResidH2Bufs - 1);
+                }
+                tmem_ld_wait();
+                if (c + 1 == kChunks) {   // accumulator stage drained into registers: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+                mbar_wait(&rbar[g % kResidH2Bufs], (g / kResidH2Bufs) & 1);
+                const uint32_t hrow = wbase + (g % kResidH2Bufs) * 4096 + lane * 64;
+                const uint32_t lrow = hrow + 2048;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {     // 16-byte slot j = columns 8 j .. 8 j + 7 of this thread's row
+                    const uint32_t so = static_cast<uint32_t>((j ^ ((lane >> 1) & 3)) << 4);
+                    const uint4 hh = lds_v4u(hrow + so), ll = lds_v4u(lrow + so);
+                    const uint32_t hs[4] = {hh.x, hh.y, hh.z, hh.w}, ls[4] = {ll.x, ll.y, ll.z, ll.w};
+                    const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+                    const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    uint32_t nh[4], nl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 hf = unpack_op16x2(hs[e]), lf = unpack_op16x2(ls[e]);
+                        const float v0 = (hf.x + lf.x) + (__uint_as_float(acc[8 * j + 2 * e]) + bs[2 * e]);
+                        const float v1 = (hf.y + lf.y) + (__uint_as_float(acc[8 * j + 2 * e + 1]) + bs[2 * e + 1]);
+                        split_op16x2(v0, v1, nh[e], nl[e]);
+                        s1 += v0 + v1;
+                        s2 += v0 * v0 + v1 * v1;
+                    }
+                    sts_v4u(hrow + so, make_uint4(nh[0], nh[1], nh[2], nh[3]));
+                    sts_v4u(lrow + so, make_uint4(nl[0], nl[1], nl[2], nl[3]));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmap_out, wbase + (g % kResidH2Bufs) * 4096, col0, m_base);
+                    tma_store_2d(&tmap_out16, wbase + (g % kResidH2Bufs) * 4096 + 2048, col0, m_base);
+                    tma_store_commit();
+                }
+                if (c + 1 == kChunks) {   // this thread's row is complete for this half tile
+                    const int m = m_base + lane;
+                    const int n_blk = (col0 - half * (BLOCK_N / 2)) / BLOCK_N;
+                    if (m < p.m_valid) p.stats_out[static_cast<size_t>(n_blk * 2 + half) * p.stats_ld + m] = make_float2(s1, s2);
+                    s1 = s2 = 0.f;
+                }
+            }
         } else {
             const int half = ew >> 2;               // which half of the tile's columns this warp drains
             constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
@@ -811,7 +922,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
     }
 
-    if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid) {
+    if constexpr ((T::kF16 && MCM_GEMM_F16_TMA_STORE) || T::kTmaResid || T::kTmaResidH2) {
         if (warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores must have completed before the CTA exits
     }
     __syncwarp();

@@ -117,13 +117,14 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // Finish the embeddings after the patch GEMM has written  patch . W + pos  into the patch rows of x:
 //   row b*S      <- class_embedding + pos[0]                    (HF:212-213,217)
 //   every row    <- pre_layrnorm(row)                            (HF:677)   -> x   (fp32 residual stream)
-// plus what the LayerNorm-folded q/k/v projection of layer 0 reads (gemm_tcgen05.cuh): the fp16 copy of
-// the row (xh) and its (sum, sum of squares) as part 0 of the row statistics.
+// The rows leave as the fp16 (hi, lo) pair the residual stream is kept in (xh, xh_lo; gemm_tcgen05.cuh
+// EPI_BIAS_RESID_H2_*) -- hi is what the LayerNorm-folded q/k/v projection of layer 0 reads -- plus their
+// (sum, sum of squares) as part 0 of the row statistics.
 template <int VEC>
 __global__ void __launch_bounds__(kRowThreads)
 embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, op16_t* __restrict__ xh_lo, float2* __restrict__ stats,
                     const float* __restrict__ cls, const float* __restrict__ pos, const float* __restrict__ pre_g,
-                    const float* __restrict__ pre_b, int M, int S, float eps) {
+                    const float* __restrict__ pre_b, int M, int S, float eps, int write_x) {
     constexpr int D = 128 * VEC;
     pdl_launch_dependents();
     pdl_wait();
@@ -138,12 +139,10 @@ embed_finish_kernel(float* __restrict__ x, op16_t* __restrict__ xh, op16_t* __re
         r.load(x + static_cast<size_t>(row) * D, lane);
     }
     r.layernorm(pre_g, pre_b, eps, lane);
-    r.store_f32(x + static_cast<size_t>(row) * D, lane);
+    if (write_x) r.store_f32(x + static_cast<size_t>(row) * D, lane);     // only the per-kernel test hook reads it back
     if (xh != nullptr) {
-        if (xh_lo != nullptr)      // split-precision mode
-            r.store_f16_split(xh + static_cast<size_t>(row) * D, xh_lo + static_cast<size_t>(row) * D, lane);
-        else
-            r.store_f16(xh + static_cast<size_t>(row) * D, lane);
+        // the residual stream from here on: an fp16 (hi, lo) pair; hi is what the q/k/v projection reads
+        r.store_f16_split(xh + static_cast<size_t>(row) * D, xh_lo + static_cast<size_t>(row) * D, lane);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {

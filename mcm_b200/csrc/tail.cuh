@@ -16,27 +16,36 @@ namespace mcm {
 
 enum ScoreKind : int { SCORE_MCM = 0, SCORE_MAX_LOGIT = 1, SCORE_ENERGY = 2, SCORE_ENTROPY = 3, SCORE_VAR = 4 };
 
-// ---- stage 1: post_layernorm of the pooled rows: x row (img * row_stride) -> ln [b, D] ----
+// ---- stage 1: post_layernorm of the pooled rows: row (img * row_stride) of x (fp32), or of the residual pair
+//      xh + xl when x is null (the forward keeps the residual stream as fp16 (hi, lo) pairs) -> ln [b, D] ----
 __global__ void __launch_bounds__(256)
-pooled_layernorm_kernel(const float* __restrict__ x, size_t row_stride, int D, int b, const float* __restrict__ g,
-                        const float* __restrict__ be, float eps, float* __restrict__ ln) {
+pooled_layernorm_kernel(const float* __restrict__ x, const op16_t* __restrict__ xh, const op16_t* __restrict__ xl, size_t row_stride,
+                        int D, int b, const float* __restrict__ g, const float* __restrict__ be, float eps, float* __restrict__ ln) {
     pdl_launch_dependents();
     pdl_wait();
     const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (img >= b) return;
-    const float* row = x + static_cast<size_t>(img) * row_stride;
+    const size_t r0 = static_cast<size_t>(img) * row_stride;
+    auto at = [&](int c) -> float {
+        if (x != nullptr) return x[r0 + c];
+#ifdef MCM_OP_BF16
+        return __bfloat162float(xh[r0 + c]) + __bfloat162float(xl[r0 + c]);
+#else
+        return __half2float(xh[r0 + c]) + __half2float(xl[r0 + c]);
+#endif
+    };
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += row[c];
+    for (int c = lane; c < D; c += 32) s += at(c);
     const float mean = warp_sum(s) / D;
     float q = 0.f;
     for (int c = lane; c < D; c += 32) {
-        const float d = row[c] - mean;
+        const float d = at(c) - mean;
         q += d * d;
     }
     const float rstd = rsqrtf(warp_sum(q) / D + eps);
     for (int c = lane; c < D; c += 32)
-        ln[static_cast<size_t>(img) * D + c] = (row[c] - mean) * rstd * __ldg(g + c) + __ldg(be + c);
+        ln[static_cast<size_t>(img) * D + c] = (at(c) - mean) * rstd * __ldg(g + c) + __ldg(be + c);
 }
 
 // ---- stages 2, 3: C[M, N] = A[M, Kd] . B[N, Kd]^T in fp32 on the CUDA cores ----

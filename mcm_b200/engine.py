@@ -389,6 +389,17 @@ class McmEngine:
                                                     C.byref(parts), self._stream()))
         return out, out16, stats[:parts.value]
 
+    def dbg_gemm_resid_h2(self, a, w, bias, x_hi, x_lo):
+        """(x_hi, x_lo) <- split(x_hi + x_lo + A @ W^T + bias) in place (the residual epilogue of the forward);
+        returns the partial row statistics [parts, M, 2]."""
+        M, K = a.shape
+        N = w.shape[0]
+        stats = torch.zeros((N // 64, M, 2), dtype=torch.float32, device=self.device)
+        parts = C.c_int32(0)
+        self._check(self._lib.mcm_dbg_gemm_resid_h2(self._h, _ptr(a.contiguous()), _ptr(w.contiguous()), _ptr(bias), _ptr(x_hi),
+                                                    _ptr(x_lo), _ptr(stats), M, N, K, C.byref(parts), self._stream()))
+        return stats[:parts.value]
+
     def dbg_gemm_ln(self, a, w16, d, c, stats, row_len: int, gelu: bool = False):
         """[quick_gelu](LayerNorm(rows) @ W^T + b) through the folded projection; stats: [parts, M, 2] fp32."""
         M, K = a.shape
@@ -444,6 +455,10 @@ class McmEngine:
     def set_cuda_graph(self, on: bool) -> None:
         """Replay the forward from a CUDA graph captured per (input buffer, batch size, options): small batches."""
         self._check(self._lib.mcm_set_option(self._h, _lib.OPT_CUDA_GRAPH, 1 if on else 0))
+
+    def set_attention_v1(self, on: bool) -> None:
+        """A/B measurements: the round-1 attention kernel instead of the cooperative one (same results)."""
+        self._check(self._lib.mcm_set_option(self._h, _lib.OPT_ATTENTION_V1, 1 if on else 0))
 
     def allgather_scores(self, nccl_comm: int, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """``mcm_allgather_scores``: one NCCL all-gather of this rank's (padded) score vector on the current stream;

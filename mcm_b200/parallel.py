@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_len", "gather_scores", "world", "NcclComm", "gather_scores_nccl"]
+__all__ = ["shard_bounds", "shard_len", "gather_scores", "world", "NcclComm", "gather_scores_nccl", "pin_to_gpu_numa"]
 
 
 def world() -> Tuple[int, int]:
@@ -131,3 +131,39 @@ def gather_scores_nccl(engine, comm: NcclComm, local: torch.Tensor, n: int) -> n
     recv = torch.empty((comm.world_size * per,), dtype=torch.float32, device=engine.device)
     engine.allgather_scores(comm.handle, send, recv)
     return recv[:n].cpu().numpy().astype(np.float32, copy=True)
+
+
+def pin_to_gpu_numa(device: int) -> Optional[list]:
+    """Bind this process (one rank per GPU) to the CPU cores of its GPU's NUMA node: the pinned host buffers of the
+    end-to-end path are then allocated on, and copied from, the memory next to that GPU's PCIe root, instead of eight
+    ranks pulling pixels through one socket.  Returns the CPU list it bound to, or None when the topology cannot be
+    read (single-socket boxes, containers without sysfs) -- never an error."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            bus = f"{int(getattr(pr, 'pci_domain_id', 0)):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else str(bus)).lower()
+            if len(bus.split(":")[0]) == 8:            # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+                bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = []
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

@@ -194,6 +194,28 @@ def ood_scores(images, sd, cfg: VisionCfg, bank, T=1, score="MCM", batch=64, dty
     return np.concatenate(out, axis=0)[: images.shape[0]].copy()
 
 
+@torch.no_grad()
+def ood_scores_as_shipped(images, sd, cfg: VisionCfg, text_model, tokenizer, test_labels, T=1, score="MCM", batch=256):
+    """The loop of utils/detection_util.py:209-249 AS SHIPPED: the prompts are tokenised and the whole text tower is run
+    again for EVERY image batch (:228-231), the [b, K] softmax is reduced on the host (:236,248).  The vision side is this
+    module's restatement; the text side is the HuggingFace text tower the reference itself calls (``text_model`` needs
+    ``get_text_features(input_ids=, attention_mask=)``).  Same values as :func:`ood_scores` with the bank pre-encoded --
+    eval() + no_grad make the text tower deterministic -- at the reference's own cost; used by bench.py's cpu_baseline."""
+    images = torch.as_tensor(images)
+    sdc = {k: v.float() for k, v in sd.items() if k.startswith("vision_model.") or k == "visual_projection.weight"}
+    out = []
+    for s in range(0, images.shape[0], batch):
+        f = image_features(images[s:s + batch].float(), sdc, cfg)
+        tok = tokenizer([f"a photo of a {c}" for c in test_labels], padding=True, return_tensors="pt")     # :228
+        tf = text_model.get_text_features(input_ids=tok["input_ids"], attention_mask=tok["attention_mask"])
+        tf = (tf.pooler_output if hasattr(tf, "pooler_output") else tf).float()                             # :229-230
+        tf = tf / tf.norm(dim=-1, keepdim=True)                                                             # :231
+        out.append(np.asarray(scores_from_features(f, tf, T, score), dtype=np.float32))
+    if not out:
+        return np.zeros((0,), dtype=np.float32)
+    return np.concatenate(out, axis=0)[: images.shape[0]].copy()
+
+
 # ----------------------------------------------------------------------------
 # metric layer, utils/detection_util.py:47-119
 # ----------------------------------------------------------------------------

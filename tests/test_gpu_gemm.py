@@ -116,3 +116,32 @@ def test_gemm_layernorm_fold_matches_torch(engine_factory, M, D, K1, N2, gelu, i
     err = (y.float() - y_ref).abs().max().item()
     rel = ((y.float() - y_ref).abs() / (y_ref.abs() + 1.0)).max().item()
     assert err <= 6e-2 and rel <= 1e-2, f"M={M} D={D} N={N2}: max|d|={err} rel={rel}"
+
+
+# ---- the residual epilogue the forward runs: the residual stream is an fp16 (hi, lo) pair updated in place
+#      (EPI_BIAS_RESID_H2_LN: through TMA for K <= 1024, through the LSU for longer K) ----
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (200, 128, 64), (1576, 768, 768), (1576, 768, 3072), (197 * 160, 768, 768),
+                                   (197 * 40, 1024, 4096), (300, 384, 1088)])
+def test_gemm_residual_pair_in_place(engine_factory, M, N, K):
+    eng, _, _ = engine_factory("tiny", 5, 8)
+    g = torch.Generator(device="cuda").manual_seed(M + 5 * N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.float16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.float16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g) * (0.5 + 3 * torch.rand(M, 1, device="cuda", generator=g)) \
+        + torch.randn(M, 1, device="cuda", generator=g)
+    x_hi = x.to(torch.float16)
+    x_lo = (x - x_hi.float()).to(torch.float16)
+    x_in = x_hi.double() + x_lo.double()                      # the value the pair carries (~22 bits of x)
+    ref = x_in + a.double() @ w.double().t() + bias.double()
+    stats = eng.dbg_gemm_resid_h2(a, w, bias, x_hi, x_lo)
+    torch.cuda.synchronize()
+    got = x_hi.double() + x_lo.double()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3, err                                     # fp32 accumulation order (same bound as the fp32 epilogue)
+    # the pair is a proper split of the fp32 result: hi = fp16(v), so |lo| = |v - hi| <= half an ulp of hi (2^-11 relative)
+    assert ((x_hi.double() - got).abs() <= 2.0 ** -11 * got.abs() + 1e-7).all()
+    assert ((got - ref).abs() / (ref.abs() + 1e-3)).median().item() <= 2e-6
+    s = stats.sum(0).double()
+    assert torch.allclose(s[:, 0], got.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (got * got).sum(1), rtol=1e-4, atol=1e-2)

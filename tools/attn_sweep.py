@@ -16,17 +16,24 @@ if os.environ.get("SWEEP_LIB"):       # A/B variant built by mcm_b200.build.buil
 cfg = synth.CFGS["tiny"]
 eng = McmEngine.from_state_dict(synth.synth_vision_state_dict(cfg, 5), cfg, max_batch=4)
 shapes = [tuple(int(v) for v in c.split(",")) for c in os.environ.get("SWEEP_SHAPES", "256,197,12;256,50,12;64,197,12;128,257,16").split(";")]
+kernels = [k for k in os.environ.get("SWEEP_KERNELS", "coop,v1").split(",") if k]
 for b, S, H in shapes:
     qkv = (torch.randn(b * S, 3 * H * 64, device="cuda") * 1.5).to(torch.float16)
-    for _ in range(3):
-        eng.dbg_attention(qkv, b, S, H)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        eng.dbg_attention(qkv, b, S, H)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / 20
-    print(json.dumps(dict(lib=os.path.basename(os.environ.get("SWEEP_LIB", "default")), b=b, S=S, H=H,
-                          us=us, tflops=4.0 * b * H * S * S * 64 / us / 1e6)), flush=True)
+    outs = {}
+    for kern in kernels:
+        eng.set_attention_v1(kern == "v1")
+        for _ in range(3):
+            outs[kern] = eng.dbg_attention(qkv, b, S, H)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            eng.dbg_attention(qkv, b, S, H)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 20
+        line = dict(lib=os.path.basename(os.environ.get("SWEEP_LIB", "default")), kernel=kern, b=b, S=S, H=H,
+                    us=us, tflops=4.0 * b * H * S * S * 64 / us / 1e6)
+        if len(outs) == 2:
+            line["max_abs_diff_between_kernels"] = float((outs["coop"].float() - outs["v1"].float()).abs().max())
+        print(json.dumps(line), flush=True)
