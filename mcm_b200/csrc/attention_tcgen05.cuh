@@ -34,7 +34,7 @@
 // build): one unit takes ~7.7 k cycles end to end -- row max 1.4 k, exp2 pass 3.1 k (the warp's own
 // instruction stream, MUFU 53 % busy), and ~3.2 k of hand-offs (barrier hops, issuing 13 P.V UMMAs,
 // draining O) -- with two units in flight per SM (TMEM holds two S buffers).  Tried and rejected: software-
-// pipelined TMEM loads (MCM_ATC_PIPE, +13 %), one pass per row with a lazily raised maximum (MCM_ATC_SINGLE_PASS,
+// pipelined TMEM loads (+13 %), one pass per row with a lazily raised reference maximum (
 // +6 %), two threads per row, one MMA issuer warp per buffer, forcing the two groups out of phase (all +-5 %), and
 // moving the 69 rows beyond the first 128 of ViT-B/16 to four mma.sync warps so that an item needs ONE unit (2.2 x
 // slower: a 16-row mma.sync tile over 208 keys takes one warp ~8 k cycles, five of them per item on four warps).
@@ -51,14 +51,8 @@
 #include <cuda.h>
 #include "ptx.cuh"
 
-#ifndef MCM_ATC_SINGLE_PASS
-#define MCM_ATC_SINGLE_PASS 0   // 1: one TMEM pass per score row with a lazily updated reference maximum (see atc_rescale_p)
-#endif
 #ifndef MCM_ATC_SHARED_O
 #define MCM_ATC_SHARED_O 1      // 0: O inside each score buffer for every shape (A/B builds)
-#endif
-#ifndef MCM_ATC_PIPE
-#define MCM_ATC_PIPE 0   // 1: software-pipeline the pass-2 TMEM loads (measured slower: more registers, no MUFU gain)
 #endif
 
 namespace mcm {
@@ -108,6 +102,16 @@ __host__ __device__ inline int atc_kv_box_rows(int S) { return S <= 64 ? 64 : at
 __host__ __device__ inline int atc_smem_bytes(int keys_pad) {
     return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + 2 * kAtcXBytes + kAtcStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
 }
+
+// 3D tiled store shared -> global (bulk async group of the issuing thread); elements outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void atc_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void atc_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void atc_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- extra tcgen05 PTX ----
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -206,26 +210,72 @@ __device__ __forceinline__ void atc_chunk_exp(const uint32_t (&v)[32], int k0, i
     tmem_st_32x32b_x16(t_p, pk);
 }
 
-// Single-pass softmax (MCM_ATC_SINGLE_PASS): every 32-key chunk is read from tensor memory ONCE.  The row keeps
-// a reference maximum m (scaled units) that is an actual score of the row; a chunk whose maximum exceeds m + 8
-// raises it and the probabilities already written (fp16 in TMEM) and the partial sums are multiplied by
-// 2^(m_old - m_new) -- rare: a later key has to beat every earlier one by a factor of 256.  All probabilities
-// stay <= 2^8 (exact in fp16's range), the row's largest one is >= 1, and O / rowsum is independent of m.
-// f: this lane's factor (1 for rows that keep their maximum); n16: number of 16-column P chunks written so far.
-__device__ __forceinline__ void atc_rescale_p(uint32_t t_p, int n16, float f) {
-    tmem_st_wait();
-    for (int i = 0; i < n16; ++i) {
-        uint32_t pk[16];
-        tmem_ld_32x32b_x16(t_p + 16 * i, pk);
+// The two softmax passes of one warp (one query row per thread) over its score columns in tensor memory:
+//   pass 1: row maximum (TMEM loads two chunks at a time so that their latencies overlap),
+//   pass 2: p = 2^(s * c - max * c), written back over the first half of the score columns as packed fp16, row sum.
+// NFULL >= 0: the number of 32-key chunks is a compile-time constant and every one of them is fully valid (the caller
+// checked S_tc >= 32 * NFULL), so the loops unroll and the chunk addresses are immediates; REM16: a trailing 16-key chunk,
+// the only place padded keys (>= S_tc) can sit.  NFULL < 0: run-time chunk count, any chunk may hold padded keys.
+// s_x: raw score of the extra key (ViT-L/14's 257th token), -INFINITY if there is none; on return the probability of that
+// key rounded like the P operand (0 if none).  Returns the row sum.
+template <int NFULL, bool REM16>
+__device__ __forceinline__ float atc_two_pass(uint32_t t_sr, uint32_t t_pw, int nfull_rt, bool rem16_rt, int S_tc, float c, float& s_x) {
+    const int nfull = NFULL >= 0 ? NFULL : nfull_rt;
+    const bool rem16 = NFULL >= 0 ? REM16 : rem16_rt;
+    const int s_lim = NFULL >= 0 ? (1 << 30) : S_tc;       // compile-time shapes: full chunks hold valid keys only
+    float mx = s_x;
+#pragma unroll 1
+    for (int ch = 0; ch < nfull; ch += 2) {
+        uint32_t va[32], vb[32];
+        const bool two = ch + 1 < nfull;
+        tmem_ld_32x32b_x32(t_sr + ch * 32, va);
+        if (two) tmem_ld_32x32b_x32(t_sr + ch * 32 + 32, vb);
+        tmem_ld_wait();
+        mx = atc_chunk_max(va, ch * 32, s_lim, mx);
+        if (two) mx = atc_chunk_max(vb, ch * 32 + 32, s_lim, mx);
+    }
+    if (rem16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const float2 v = unpack_op16x2(pk[e]);
-            pk[e] = pack_op16x2(v.x * f, v.y * f);
-        }
-        tmem_st_32x32b_x16(t_p + 16 * i, pk);
+        for (int e = 0; e < 16; ++e)
+            if (nfull * 32 + e < S_tc) mx = fmaxf(mx, __uint_as_float(v[e]));
     }
-    tmem_st_wait();
+    const float mc = mx * c;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll (NFULL > 0 && NFULL % 3 == 0 ? 3 : 2)
+    for (int ch = 0; ch < nfull; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_sr + ch * 32, v);
+        tmem_ld_wait();
+        atc_chunk_exp(v, ch * 32, s_lim, c, mc, sum0, sum1, t_pw + ch * 16);
+    }
+    if (rem16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k0 = nfull * 32 + 2 * e;
+            const float p0 = (k0 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
+            const float p1 = (k0 + 1 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
+            sum0 += p0;
+            sum1 += p1;
+            pk[e] = pack_op16x2(p0, p1);
+        }
+        tmem_st_32x32b_x8(t_pw + nfull * 16, pk);
+    }
+    float sum = sum0 + sum1;
+    if (s_x != -INFINITY) {   // the extra key: its probability, rounded like the P operand
+        const float px = ex2_approx(fmaf(s_x, c, -mc));
+        sum += px;
+        s_x = unpack_op16x2(pack_op16x2(px, 0.f)).x;
+    } else {
+        s_x = 0.f;
+    }
+    return sum;
 }
 
 // ===== TMA producer (one elected thread of warp 0): K / V of every item, the Q tile of every unit =====
@@ -417,9 +467,12 @@ __device__ __forceinline__ void atc_tail_rows(const AtcParams& p, const AtcSmem&
     }
 }
 
+// NFULL / REM16: compile-time chunk structure of the softmax passes (atc_two_pass): <6, true> ViT-B/16 (keys_pad 208, at
+// least 192 valid keys), <8, false> ViT-L/14 (keys_pad 256), <-1, *> any other shape at run time (pair mode, tests).
+template <int NFULL, bool REM16>
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                         const __grid_constant__ CUtensorMap tmap_x, const AtcParams p) {
+                         const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_o, const AtcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kv_bytes = p.keys_pad * 128;                       // one K or V tile
@@ -457,6 +510,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
         if (p.n_extra > 0) tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_o);
         // with an extra key the softmax warps read their q rows from the Q tile and k / v of the extra token from the
         // x box: they release the Q stage and the K / V stage together with the MMA thread's commits
         for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], p.n_extra > 0 ? 5 : 1); }
@@ -586,133 +640,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 0);       // S ready
             tcgen05_fence_after();
             float row_sum = 1.f;
-#if MCM_ATC_SINGLE_PASS
             if (warp_valid) {
-                float m = -INFINITY;            // reference maximum, scaled (raw score * c)
-                float sum0 = 0.f, sum1 = 0.f;
-                for (int ch = 0; ch < nfull; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_sr + ch * 32, v);
-                    tmem_ld_wait();
-                    float cm = atc_chunk_max(v, ch * 32, S_tc, -INFINITY);
-                    if (ch == 0 && p.n_extra > 0) cm = fmaxf(cm, s_x);
-                    cm *= c;
-                    const bool raise = cm > m + 8.0f;
-                    if (__any_sync(0xffffffffu, raise)) {
-                        const float f = raise ? ex2_approx(m - cm) : 1.0f;     // m = -inf (first chunk): f = 0, nothing to scale
-                        if (ch > 0) atc_rescale_p(t_pw, ch, f);
-                        sum0 *= f;
-                        sum1 *= f;
-                        if (raise) m = cm;
-                    }
-                    atc_chunk_exp(v, ch * 32, S_tc, c, m, sum0, sum1, t_pw + ch * 16);
-                }
-                if (rem16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
-                    tmem_ld_wait();
-                    float cm = -INFINITY;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (nfull * 32 + e < S_tc) cm = fmaxf(cm, __uint_as_float(v[e]));
-                    if (nfull == 0 && p.n_extra > 0) cm = fmaxf(cm, s_x);
-                    cm *= c;
-                    const bool raise = cm > m + 8.0f;
-                    if (__any_sync(0xffffffffu, raise)) {
-                        const float f = raise ? ex2_approx(m - cm) : 1.0f;
-                        if (nfull > 0) atc_rescale_p(t_pw, nfull, f);
-                        sum0 *= f;
-                        sum1 *= f;
-                        if (raise) m = cm;
-                    }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k0 = nfull * 32 + 2 * e;
-                        const float p0 = (k0 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -m)) : 0.f;
-                        const float p1 = (k0 + 1 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -m)) : 0.f;
-                        sum0 += p0;
-                        sum1 += p1;
-                        pk[e] = pack_op16x2(p0, p1);
-                    }
-                    tmem_st_32x32b_x8(t_pw + nfull * 16, pk);
-                }
-                tmem_st_wait();
-                row_sum = sum0 + sum1;
-                if (p.n_extra > 0) {   // s_x becomes the probability of the extra key, rounded like the P operand
-                    const float px = ex2_approx(fmaf(s_x, c, -m));
-                    row_sum += px;
-                    s_x = unpack_op16x2(pack_op16x2(px, 0.f)).x;
-                }
-            }
-#else
-            if (warp_valid) {
-                // ---- pass 1: row max over the S valid keys (only the last chunk can hold padded keys);
-                //      TMEM loads are issued two chunks at a time so their latencies overlap ----
-                float mx = -INFINITY;
-                for (int ch = 0; ch < nfull; ch += 2) {
-                    uint32_t va[32], vb[32];
-                    const bool two = ch + 1 < nfull;
-                    tmem_ld_32x32b_x32(t_sr + ch * 32, va);
-                    if (two) tmem_ld_32x32b_x32(t_sr + ch * 32 + 32, vb);
-                    tmem_ld_wait();
-                    mx = atc_chunk_max(va, ch * 32, S_tc, mx);
-                    if (two) mx = atc_chunk_max(vb, ch * 32 + 32, S_tc, mx);
-                }
-                if (rem16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (nfull * 32 + e < S_tc) mx = fmaxf(mx, __uint_as_float(v[e]));
-                }
-                if (p.n_extra > 0) mx = fmaxf(mx, s_x);
-                const float mc = mx * c;
-                if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 1);   // pass 1 done
-                // ---- pass 2: p = 2^(s * c - max * c); P (fp16) overwrites the first half of the S columns.
-                //      Software-pipelined: the TMEM load of chunk i + 1 is in flight while chunk i is in the MUFU ----
-                float sum0 = 0.f, sum1 = 0.f;
-#if MCM_ATC_PIPE
-                {
-                    uint32_t va[32], vb[32];
-                    if (nfull > 0) tmem_ld_32x32b_x32(t_sr, va);
-                    for (int ch = 0; ch < nfull; ch += 2) {
-                        tmem_ld_wait();
-                        const bool two = ch + 1 < nfull;
-                        if (two) tmem_ld_32x32b_x32(t_sr + ch * 32 + 32, vb);
-                        atc_chunk_exp(va, ch * 32, S_tc, c, mc, sum0, sum1, t_pw + ch * 16);
-                        if (two) {
-                            tmem_ld_wait();
-                            if (ch + 2 < nfull) tmem_ld_32x32b_x32(t_sr + ch * 32 + 64, va);
-                            atc_chunk_exp(vb, ch * 32 + 32, S_tc, c, mc, sum0, sum1, t_pw + ch * 16 + 16);
-                        }
-                    }
-                }
-#else
-                for (int ch = 0; ch < nfull; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_sr + ch * 32, v);
-                    tmem_ld_wait();
-                    atc_chunk_exp(v, ch * 32, S_tc, c, mc, sum0, sum1, t_pw + ch * 16);
-                }
-#endif
-                if (rem16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_sr + nfull * 32, v);
-                    tmem_ld_wait();
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k0 = nfull * 32 + 2 * e;
-                        const float p0 = (k0 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
-                        const float p1 = (k0 + 1 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
-                        sum0 += p0;
-                        sum1 += p1;
-                        pk[e] = pack_op16x2(p0, p1);
-                    }
-                    tmem_st_32x32b_x8(t_pw + nfull * 16, pk);
-                }
+                if (p.n_extra == 0) s_x = -INFINITY;
+                row_sum = atc_two_pass<NFULL, REM16>(t_sr, t_pw, nfull, rem16, S_tc, c, s_x);
+                if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 1);   // both passes issued
                 if (pair) {     // probability 0 for the 64 keys of the other item (for half 0 these columns held this row's
                                 // own scores 32..63: consumed by now)
                     uint32_t zero[16];
@@ -722,14 +653,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     tmem_st_32x32b_x16(t_s + (1 - half) * 32 + 16, zero);
                 }
                 tmem_st_wait();
-                row_sum = sum0 + sum1;
-                if (p.n_extra > 0) {   // s_x becomes the probability of the extra key, rounded like the P operand
-                    const float px = ex2_approx(fmaf(s_x, c, -mc));
-                    row_sum += px;
-                    s_x = unpack_op16x2(pack_op16x2(px, 0.f)).x;
-                }
             }
-#endif
             tcgen05_fence_before();
             __syncwarp();
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 2);       // pass 2 done
@@ -741,6 +665,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tcgen05_fence_after();
             if (warp_valid) {
                 const float inv = 1.0f / row_sum;
+                // the bulk store of this warp's previous unit has read the staging tile (issued a whole unit ago)
+                if (lane == 0) atc_store_wait_read();
+                __syncwarp();
 #pragma unroll
                 for (int hc = 0; hc < 2; ++hc) {
                     uint32_t v[32];
@@ -767,9 +694,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         w.z = pack_op16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
                         w.w = pack_op16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
                         const int chunk = hc * 4 + q;
-                        sts_v4u(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4), w);
+                        sts_v4u(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4), w);      // the SWIZZLE_128B image of the output box
                     }
                 }
+                fence_proxy_async_smem();
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -777,23 +705,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             if (lane == 0) {
                 mbar_arrive(&s_free[g]);                            // TMEM buffer may be overwritten by the next QK^T
                 if (p.n_extra > 0) mbar_arrive(&kv_empty[iu & 1]);  // this warp is done with the x box of the K / V stage
-            }
-            if (warp_valid) {
-                const int cq = lane & 7;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = (lane >> 3) + 4 * i;
-                    const int row = wrow0 + r;
-                    if (row < p.S) {
-                        const uint4 w = lds_v4u(stg + r * 128 + ((cq ^ (r & 7)) << 4));
-                        *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(img) * p.S + row) * D + h * 64 + cq * 8) = w;
-                    }
+                // 32 rows x 64 head dims of (image, head) leave as ONE bulk store; the output map is 3-D ([image][token][D]),
+                // so rows beyond the image's S tokens (padded query rows) are clipped by the TMA unit
+                if (warp_valid) {
+                    tma_store_3d(&tmap_o, stg, h * 64, wrow0, img);
+                    atc_store_commit();
                 }
             }
             __syncwarp();
         }
     }
 
+    if (warp >= 2 && warp < 10 && lane == 0) atc_store_wait_all();   // bulk stores must have completed before the CTA exits
     __syncwarp();
     tcgen05_fence_before();
     __syncthreads();

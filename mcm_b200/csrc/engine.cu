@@ -114,7 +114,7 @@ struct McmHandle {
     int precision = MCM_PRECISION_FP16;
     op16_t *patches_lo = nullptr, *xh_lo = nullptr, *qkv_lo = nullptr, *attn_lo = nullptr, *hid_lo = nullptr;
     CUtensorMap tm_patches_lo, tm_xh_lo, tm_attn_lo, tm_hid_lo;
-    CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
+    CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x, tm_attn_o;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
     bool attn_v1 = true;               // MCM_OPT_ATTENTION_V1: the round-1 kernel (one softmax group per TMEM buffer)
     bool cls_shortcut = true;
@@ -164,6 +164,7 @@ struct McmHandle {
     };
     std::map<GraphKey, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (executable graph, kernels in it)
     float* t_scores = nullptr;    // [max_batch] scores of a graph replay (copied to the caller's buffer behind it)
+    cudaStream_t s_capture = nullptr;
 
     // optional per-launch timing (mcm_profile_*): events bracket every launch of a forward
     bool prof_on = false;
@@ -592,8 +593,9 @@ int launch_attention_mma(McmHandle* h, const op16_t* qkv, const op16_t* qkv_lo, 
 }
 
 // tq / tkv: tensor maps over the fused QKV buffer with 128-row and keys_pad-row boxes
-int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tx, const op16_t* qkv, op16_t* out,
-                     int b, int S, int H, cudaStream_t st) {
+// to: 3-D map over the output [images][S][H * 64] with 32-row boxes (the O tiles leave as bulk stores, clipped at S)
+int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tx, const CUtensorMap& to,
+                     const op16_t* qkv, op16_t* out, int b, int S, int H, cudaStream_t st) {
     if (b <= 0) return MCM_OK;
     if (h->attn_mma || S > kAtcMaxS) return launch_attention_mma(h, qkv, nullptr, out, nullptr, b, S, H, st);
     AtcParams p{};
@@ -619,8 +621,13 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
     if (h->attn_v1) {
         const int smem = atc_smem_bytes(p.keys_pad);
-        MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_tcgen05_kernel), smem));
-        MCM_CUDA(h, launch_k(attention_tcgen05_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
+        // softmax passes unrolled for the two production shapes (attention_tcgen05.cuh, atc_two_pass)
+        auto kern = attention_tcgen05_kernel<-1, false>;
+        const int s_tc = S - p.n_extra;
+        if (!p.pair_mode && p.keys_pad == 208 && s_tc >= 192) kern = attention_tcgen05_kernel<6, true>;
+        else if (!p.pair_mode && p.keys_pad == 256 && s_tc >= 256) kern = attention_tcgen05_kernel<8, false>;
+        MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(kern), smem));
+        MCM_CUDA(h, launch_k(kern, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, to, p));
     } else {
         const int smem = atc_coop_smem_bytes(p.keys_pad);
         MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_coop_kernel), smem));
@@ -794,7 +801,7 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
         if (split) {
             if ((rc = launch_attention_mma(h, h->qkv, h->qkv_lo, h->attn, h->attn_lo, b, h->S, h->H, st))) return rc;
         } else {
-            if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->tm_qkv_x, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
+            if ((rc = launch_attention(h, h->tm_qkv_q, h->tm_qkv_kv, h->tm_qkv_x, h->tm_attn_o, h->qkv, h->attn, b, h->S, h->H, st))) return rc;
         }
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_OUT, h->tm_attn, w.tm_wo, M, D, D, EPI_BIAS_RESID_H2_LN, w.bo, nullptr, nullptr, nullptr, 0, 0, st, out_a))) return rc;
         if ((rc = launch_gemm(h, MCM_PROF_GEMM_FC1, h->tm_xh, w.tm_w1, M, F, D, EPI_LN_QGELU_F16, w.d1, h->hid, nullptr, nullptr, 0, 0, st, ln2))) return rc;
@@ -1061,6 +1068,7 @@ int mcm_create(const McmConfig* cfg, McmHandle** out) {
             MCM_TRY(make_tmap(h, &h->tm_qkv_q, h->qkv, h->m_pad, 3 * D, 128));
             MCM_TRY(make_tmap_kv(h, &h->tm_qkv_kv, h->qkv, cfg->max_batch, h->S, 3 * D, atc_kv_box_rows(h->S)));
             MCM_TRY(make_tmap(h, &h->tm_qkv_x, h->qkv, h->m_pad, 3 * D, 8));
+            MCM_TRY(make_tmap_kv(h, &h->tm_attn_o, h->attn, cfg->max_batch, h->S, D, 32));
         }
     }
 #undef MCM_TRY
@@ -1076,6 +1084,7 @@ void mcm_destroy(McmHandle* h) {
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.first);
     h->graphs.clear();
     if (h->ev_busy) cudaEventDestroy(h->ev_busy);
+    if (h->s_capture) cudaStreamDestroy(h->s_capture);
     fr(h->t_scores); fr(h->wpatch_lo);
     fr(h->patches_lo); fr(h->xh_lo); fr(h->qkv_lo); fr(h->attn_lo); fr(h->hid_lo);
     fr(h->wpatch); fr(h->cls); fr(h->pos); fr(h->pre_g); fr(h->pre_b); fr(h->post_g); fr(h->post_b); fr(h->wproj);
@@ -1242,14 +1251,18 @@ int run_forward(McmHandle* h, const void* images, bool u8, int b, int mode, floa
             cudaGraph_t graph = nullptr;
             cudaGraphExec_t exec = nullptr;
             int64_t n_kernels = 0;
-            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            // capture on a stream of the handle's own: the caller's stream may be the legacy default stream (PyTorch's
+            // default), which cannot be captured; the nodes carry no stream, the replay goes to the caller's
+            cudaError_t e = cudaSuccess;
+            if (!h->s_capture) e = cudaStreamCreateWithFlags(&h->s_capture, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaStreamBeginCapture(h->s_capture, cudaStreamCaptureModeThreadLocal);
             if (e == cudaSuccess) {
                 const int64_t launches0 = h->launches;
                 rc = enqueue_forward(h, images, u8, b, mode, T, kind, mode == FWD_FEATURES ? g_out : nullptr,
-                                     mode == FWD_FEATURES ? nullptr : g_out, st);
+                                     mode == FWD_FEATURES ? nullptr : g_out, h->s_capture);
                 n_kernels = h->launches - launches0;
                 h->launches = launches0;      // recorded, not launched
-                e = cudaStreamEndCapture(st, &graph);
+                e = cudaStreamEndCapture(h->s_capture, &graph);
                 if (rc == MCM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
                 if (graph) cudaGraphDestroy(graph);
             }
@@ -1761,14 +1774,15 @@ int mcm_dbg_layernorm(McmHandle* h, const float* x, const float* g, const float*
 int mcm_dbg_attention(McmHandle* h, const void* qkv, void* o, int32_t b, int32_t S, int32_t H, void* stream) {
     if (!h || !qkv || !o) return fail(h, MCM_EINVAL, "mcm_dbg_attention: NULL argument");
     if (b <= 0 || S <= 0 || H <= 0) return fail(h, MCM_EINVAL, "mcm_dbg_attention: b, S, H must be positive");
-    CUtensorMap tq, tkv, tx;
+    CUtensorMap tq, tkv, tx, to;
     if (S <= kAtcMaxS && !h->attn_mma) {
         int rc;
         if ((rc = make_tmap(h, &tq, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 128))) return rc;
         if ((rc = make_tmap_kv(h, &tkv, qkv, static_cast<uint64_t>(b), static_cast<uint64_t>(S), 3ull * H * 64, atc_kv_box_rows(S)))) return rc;
         if ((rc = make_tmap(h, &tx, qkv, static_cast<uint64_t>(b) * S, 3ull * H * 64, 8))) return rc;
+        if ((rc = make_tmap_kv(h, &to, o, static_cast<uint64_t>(b), static_cast<uint64_t>(S), 64ull * H, 32))) return rc;
     }
-    return launch_attention(h, tq, tkv, tx, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
+    return launch_attention(h, tq, tkv, tx, to, static_cast<const op16_t*>(qkv), static_cast<op16_t*>(o), b, S, H,
                             static_cast<cudaStream_t>(stream));
 }
 
