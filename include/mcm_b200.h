@@ -188,10 +188,7 @@ enum {
     /* MCM_OPT_CUDA_GRAPH (default 0): mcm_score / mcm_image_features (and their _u8 / stream_host forms) replay a
      * CUDA graph captured per (entry point, batch size, option set) instead of ~70 individual launches:
      * for small batches, where the forward is launch-bound. */
-    MCM_OPT_CUDA_GRAPH = 3,
-    /* MCM_OPT_ATTENTION_V1 (default 0): run the round-1 attention kernel (one 4-warp softmax group per TMEM buffer)
-     * instead of the cooperative one (all eight softmax warps on one unit); same results, kept for A/B measurements. */
-    MCM_OPT_ATTENTION_V1 = 4
+    MCM_OPT_CUDA_GRAPH = 3
 };
 enum { MCM_PRECISION_FP16 = 0, MCM_PRECISION_SPLIT = 1 };
 int mcm_set_option(McmHandle* h, int32_t option, int32_t value);

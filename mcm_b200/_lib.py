@@ -20,7 +20,6 @@ PROF_KINDS = ["patchify", "gemm_patch", "embed_finish", "gemm_qkv", "attention",
 OPT_CLS_SHORTCUT = 1
 OPT_PRECISION = 2
 OPT_CUDA_GRAPH = 3
-OPT_ATTENTION_V1 = 4
 PRECISION_FP16 = 0
 PRECISION_SPLIT = 1
 PRECISIONS = {"fp16": PRECISION_FP16, "split": PRECISION_SPLIT, 0: PRECISION_FP16, 1: PRECISION_SPLIT}

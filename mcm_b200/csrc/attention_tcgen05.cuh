@@ -57,7 +57,7 @@
 
 namespace mcm {
 
-constexpr int kAtcThreads = 352;          // 11 warps: TMA, MMA, 2 x 4 softmax, tail-row warp (idle unless S > 256)
+constexpr int kAtcThreads = 384;          // 12 warps: TMA, MMA issuer of buffer 0, 2 x 4 softmax, tail-row warp (idle unless S > 256), MMA issuer of buffer 1
 constexpr int kAtcQStages = 3;
 constexpr int kAtcQBytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kAtcStagingBytes = 8 * 32 * 128; // 8 softmax warps x 32 rows x 64 fp16
@@ -218,8 +218,26 @@ __device__ __forceinline__ void atc_chunk_exp(const uint32_t (&v)[32], int k0, i
 // the only place padded keys (>= S_tc) can sit.  NFULL < 0: run-time chunk count, any chunk may hold padded keys.
 // s_x: raw score of the extra key (ViT-L/14's 257th token), -INFINITY if there is none; on return the probability of that
 // key rounded like the P operand (0 if none).  Returns the row sum.
+// P.V is issued in up to three parts of 64 keys (4 UMMA k-steps) so that most of it runs WHILE pass 2 is still producing
+// the later columns: after chunk 2 p + 1 the warp makes its P columns visible (tcgen05.wait::st + fence) and arrives on
+// its group's barrier OF THAT PART (p_part[p], p < nparts - 1; the caller signals the last part).  One barrier per part, one
+// phase per unit: arrivals carry no phase tag, so a fast warp signalling part p + 1 on a single multi-phase barrier before its
+// neighbours signalled part p would be counted towards part p (that deadlocked the first version).  atc_parts() is the split
+// both sides agree on.
+__host__ __device__ inline int atc_parts(int keys_pad, int pair_mode) {
+    const int n4 = (keys_pad >> 4) >> 2;          // whole groups of 4 k-steps
+    return pair_mode ? 1 : (n4 < 1 ? 1 : (n4 > 3 ? 3 : n4));
+}
+__device__ __forceinline__ void atc_signal_part(uint64_t* p_part, int lane) {
+    tmem_st_wait();
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_part);
+}
+
 template <int NFULL, bool REM16>
-__device__ __forceinline__ float atc_two_pass(uint32_t t_sr, uint32_t t_pw, int nfull_rt, bool rem16_rt, int S_tc, float c, float& s_x) {
+__device__ __forceinline__ float atc_two_pass(uint32_t t_sr, uint32_t t_pw, int nfull_rt, bool rem16_rt, int S_tc, float c, float& s_x,
+                                              uint64_t* p_part, int nparts, int lane) {
     const int nfull = NFULL >= 0 ? NFULL : nfull_rt;
     const bool rem16 = NFULL >= 0 ? REM16 : rem16_rt;
     const int s_lim = NFULL >= 0 ? (1 << 30) : S_tc;       // compile-time shapes: full chunks hold valid keys only
@@ -250,6 +268,8 @@ __device__ __forceinline__ float atc_two_pass(uint32_t t_sr, uint32_t t_pw, int 
         tmem_ld_32x32b_x32(t_sr + ch * 32, v);
         tmem_ld_wait();
         atc_chunk_exp(v, ch * 32, s_lim, c, mc, sum0, sum1, t_pw + ch * 16);
+        if (ch == 1 && nparts > 1) atc_signal_part(p_part, lane);          // keys 0..63 are final
+        if (ch == 3 && nparts > 2) atc_signal_part(p_part + 1, lane);      // keys 64..127 are final
     }
     if (rem16) {
         uint32_t v[16];
@@ -281,13 +301,17 @@ __device__ __forceinline__ float atc_two_pass(uint32_t t_sr, uint32_t t_pw, int 
 // ===== TMA producer (one elected thread of warp 0): K / V of every item, the Q tile of every unit =====
 struct AtcSmem {
     uint8_t *s_q, *s_kv, *s_xbox;
-    uint64_t *q_full, *q_empty, *kv_full, *kv_empty;
+    uint64_t *q_full, *q_empty, *k_full, *k_empty, *v_full, *v_empty;
     int kv_bytes;
 };
+// K and V have their own full / empty barrier pairs: the K tile of a stage is free as soon as the last Q K^T of its item
+// has run, a whole unit before the last P.V releases the V tile, so the next-but-one item's K is on its way that much earlier
+// (with one barrier pair per stage the next Q K^T waited ~2 k cycles for its K tile once P.V stopped being the bottleneck).
 __device__ __forceinline__ void atc_producer(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const CUtensorMap& tmap_x,
                                              const AtcParams& p, const AtcSmem& sm) {
     uint8_t *const s_q = sm.s_q, *const s_kv = sm.s_kv, *const s_xbox = sm.s_xbox;
-    uint64_t *const q_full = sm.q_full, *const q_empty = sm.q_empty, *const kv_full = sm.kv_full, *const kv_empty = sm.kv_empty;
+    uint64_t *const q_full = sm.q_full, *const q_empty = sm.q_empty;
+    uint64_t *const k_full = sm.k_full, *const k_empty = sm.k_empty, *const v_full = sm.v_full, *const v_empty = sm.v_empty;
     const int kv_bytes = sm.kv_bytes;
     const int n_items = p.b * p.H;
     const bool pair = p.pair_mode != 0;
@@ -295,54 +319,66 @@ __device__ __forceinline__ void atc_producer(const CUtensorMap& tmap_q, const CU
     const int upi = p.units_per_item;
     const int D = p.H * 64;
     uint32_t ic = 0, uc = 0;
+    auto load_q = [&](int h, int row0, int mt) {
+        const int qs = uc % kAtcQStages;
+        mbar_wait(&q_empty[qs], ((uc / kAtcQStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qs], kAtcQBytes);
+        tma_load_2d(s_q + qs * kAtcQBytes, &tmap_q, &q_full[qs], h * 64, row0 + mt * 128);
+        ++uc;
+    };
     for (int item = blockIdx.x; item < n_work; item += gridDim.x, ++ic) {
         const int kvs = ic & 1;
+        const uint32_t ph = ((ic >> 1) & 1) ^ 1;
         uint8_t* sk = s_kv + kvs * 2 * kv_bytes;
         if (pair) {
             // pair mode: 64-row boxes (tmap_kv) of item 2w and item 2w + 1 (the last item again if n_items is odd)
             // stacked into 128-row Q / K / V tiles; 8 KB per box keeps the 128-byte swizzle phase of the rows
-            mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes);
+            int img2[2], h2[2];
+            for (int half = 0; half < 2; ++half) {
+                const int it2 = min(2 * item + half, n_items - 1);
+                img2[half] = atc_div_h(it2, p.inv_H);
+                h2[half] = it2 - img2[half] * p.H;
+            }
+            mbar_wait(&k_empty[kvs], ph);
+            mbar_arrive_expect_tx(&k_full[kvs], kv_bytes);
+            for (int half = 0; half < 2; ++half) tma_load_3d(sk + half * 8192, &tmap_kv, &k_full[kvs], D + h2[half] * 64, 0, img2[half]);
             const int qs = uc % kAtcQStages;
             mbar_wait(&q_empty[qs], ((uc / kAtcQStages) & 1) ^ 1);
             mbar_arrive_expect_tx(&q_full[qs], kAtcQBytes);
-            for (int half = 0; half < 2; ++half) {
-                const int it2 = min(2 * item + half, n_items - 1);
-                const int img2 = atc_div_h(it2, p.inv_H), h2 = it2 - img2 * p.H;
-                tma_load_3d(sk + half * 8192, &tmap_kv, &kv_full[kvs], D + h2 * 64, 0, img2);
-                tma_load_3d(sk + kv_bytes + half * 8192, &tmap_kv, &kv_full[kvs], 2 * D + h2 * 64, 0, img2);
-                tma_load_3d(s_q + qs * kAtcQBytes + half * 8192, &tmap_kv, &q_full[qs], h2 * 64, 0, img2);
-            }
+            for (int half = 0; half < 2; ++half)
+                tma_load_3d(s_q + qs * kAtcQBytes + half * 8192, &tmap_kv, &q_full[qs], h2[half] * 64, 0, img2[half]);
             ++uc;
+            mbar_wait(&v_empty[kvs], ph);
+            mbar_arrive_expect_tx(&v_full[kvs], kv_bytes);
+            for (int half = 0; half < 2; ++half)
+                tma_load_3d(sk + kv_bytes + half * 8192, &tmap_kv, &v_full[kvs], 2 * D + h2[half] * 64, 0, img2[half]);
             continue;
         }
         const int img = atc_div_h(item, p.inv_H), h = item - img * p.H;
         const int row0 = img * p.S;
-        mbar_wait(&kv_empty[kvs], ((ic >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[kvs], 2 * kv_bytes + (p.n_extra > 0 ? kAtcXBytes : 0));
         // tmap_kv is 3-D ([image][token][3 D]): the padded key rows S .. keys_pad - 1 lie outside the image's plane and
         // arrive as ZEROS -- never another image's (or a stale batch's) rows, whose Inf / NaN would leak through 0 * V
-        tma_load_3d(sk, &tmap_kv, &kv_full[kvs], D + h * 64, 0, img);
-        tma_load_3d(sk + kv_bytes, &tmap_kv, &kv_full[kvs], 2 * D + h * 64, 0, img);
-        if (p.n_extra > 0) {
+        mbar_wait(&k_empty[kvs], ph);
+        mbar_arrive_expect_tx(&k_full[kvs], kv_bytes);
+        tma_load_3d(sk, &tmap_kv, &k_full[kvs], D + h * 64, 0, img);
+        load_q(h, row0, 0);
+        mbar_wait(&v_empty[kvs], ph);
+        mbar_arrive_expect_tx(&v_full[kvs], kv_bytes + (p.n_extra > 0 ? kAtcXBytes : 0));
+        tma_load_3d(sk + kv_bytes, &tmap_kv, &v_full[kvs], 2 * D + h * 64, 0, img);
+        if (p.n_extra > 0) {     // q | k | v of tokens 256..: travels (and is released) with the V tile
             uint8_t* sx = s_xbox + kvs * kAtcXBytes;
 #pragma unroll
             for (int part = 0; part < 3; ++part)
-                tma_load_2d(sx + part * 1024, &tmap_x, &kv_full[kvs], part * D + h * 64, row0 + 256);
+                tma_load_2d(sx + part * 1024, &tmap_x, &v_full[kvs], part * D + h * 64, row0 + 256);
         }
-        for (int mt = 0; mt < upi; ++mt, ++uc) {
-            const int qs = uc % kAtcQStages;
-            mbar_wait(&q_empty[qs], ((uc / kAtcQStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&q_full[qs], kAtcQBytes);
-            tma_load_2d(s_q + qs * kAtcQBytes, &tmap_q, &q_full[qs], h * 64, row0 + mt * 128);
-        }
+        for (int mt = 1; mt < upi; ++mt) load_q(h, row0, mt);
     }
 }
 
 // ===== tail-row warp: query rows >= 256 (ViT-L/14: the one row 256) against all S keys =====
 __device__ __forceinline__ void atc_tail_rows(const AtcParams& p, const AtcSmem& sm, int lane) {
     uint8_t *const s_kv = sm.s_kv, *const s_xbox = sm.s_xbox;
-    uint64_t *const kv_full = sm.kv_full, *const kv_empty = sm.kv_empty;
+    uint64_t *const k_full = sm.k_full, *const k_empty = sm.k_empty, *const v_full = sm.v_full, *const v_empty = sm.v_empty;
     const int kv_bytes = sm.kv_bytes;
     const int n_items = p.b * p.H;
     const int D = p.H * 64;
@@ -357,7 +393,8 @@ __device__ __forceinline__ void atc_tail_rows(const AtcParams& p, const AtcSmem&
         const uint32_t sk = smem_u32(s_kv + kvs * 2 * kv_bytes);
         const uint32_t sv = sk + kv_bytes;
         const uint32_t sx = smem_u32(s_xbox + kvs * kAtcXBytes);      // q | k | v of tokens 256.., row e swizzled by e
-        mbar_wait(&kv_full[kvs], (ic >> 1) & 1);
+        mbar_wait(&k_full[kvs], (ic >> 1) & 1);
+        mbar_wait(&v_full[kvs], (ic >> 1) & 1);
         for (int r = 256; r < p.S; ++r) {
             const int e0 = r - 256;
             // A fragments: row 0 = the query row (x box, q part), rows 1..15 = 0
@@ -463,7 +500,10 @@ __device__ __forceinline__ void atc_tail_rows(const AtcParams& p, const AtcSmem&
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&kv_empty[kvs]);     // this warp is done with the K / V stage
+        if (lane == 0) {     // this warp is done with the K / V stage
+            mbar_arrive(&k_empty[kvs]);
+            mbar_arrive(&v_empty[kvs]);
+        }
     }
 }
 
@@ -483,13 +523,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kAtcStagingBytes);
     uint64_t* q_full = bars;                       // [3]
     uint64_t* q_empty = bars + kAtcQStages;        // [3]
-    uint64_t* kv_full = bars + 2 * kAtcQStages;    // [2]
-    uint64_t* kv_empty = kv_full + 2;              // [2]
-    uint64_t* s_full = kv_full + 4;                // [2]  MMA -> softmax group: S ready
-    uint64_t* p_full = kv_full + 6;                // [2]  softmax group -> MMA: P written
-    uint64_t* o_full = kv_full + 8;                // [2]  MMA -> softmax group: O ready
-    uint64_t* s_free = kv_full + 10;               // [2]  softmax group -> MMA: O drained, buffer reusable
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(kv_full + 12);
+    uint64_t* k_full = bars + 2 * kAtcQStages;     // [2]  K tile of an item landed / its last Q K^T has run
+    uint64_t* k_empty = k_full + 2;                // [2]
+    uint64_t* v_full = k_full + 4;                 // [2]  V tile (+ x box) landed / its last P.V has run (and its readers are done)
+    uint64_t* v_empty = k_full + 6;                // [2]
+    uint64_t* s_full = k_full + 8;                 // [2]  MMA -> softmax group: S ready
+    uint64_t* o_full = k_full + 10;                // [2]  MMA -> softmax group: O ready
+    uint64_t* s_free = k_full + 12;                // [2]  softmax group -> MMA: O drained
+    uint64_t* p_part = k_full + 14;                // [2][3]  softmax group -> MMA: part p (64 keys) of P written
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(k_full + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -505,6 +547,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     // Q K^T has to wait for the drain.
     const bool shared_o = MCM_ATC_SHARED_O && p.keys_pad <= 224;
     const uint32_t buf_stride = shared_o ? static_cast<uint32_t>(p.keys_pad) : 256u;
+    // P.V is issued in nparts pieces while pass 2 still runs -- possible only when O lies outside the score buffer (inside
+    // it, columns 128..191 still hold unread scores while the first keys of P are ready)
+    const int nparts = shared_o ? atc_parts(p.keys_pad, p.pair_mode) : 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -512,11 +557,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (p.n_extra > 0) tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_o);
         // with an extra key the softmax warps read their q rows from the Q tile and k / v of the extra token from the
-        // x box: they release the Q stage and the K / V stage together with the MMA thread's commits
+        // x box (which travels with the V tile): they release the Q stage and the V stage together with the MMA thread's
+        // commits; the tail-row warp reads K and V
         for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], p.n_extra > 0 ? 5 : 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], p.n_extra > 0 ? 2 + 4 * upi : 1);   // + tail-row warp + 4 softmax warps per unit
-            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+            // every unit of an item commits once on its K tile (after its Q K^T) and once on its V tile (after its P.V): the
+            // units of one item are issued by different threads, and a commit only tracks the issuing thread's MMAs
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], upi + (p.n_extra > 0 ? 1 : 0));            // + tail-row warp
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], upi + (p.n_extra > 0 ? 1 + 4 * upi : 0));  // + tail-row warp + 4 softmax warps per unit
+            mbar_init(&s_full[i], 1);
+            for (int q = 0; q < 3; ++q) mbar_init(&p_part[3 * i + q], 4);
             mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
         }
         fence_barrier_init();
@@ -529,61 +579,69 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();   // everything above overlapped the predecessor's tail; global data is touched only below
 
-    const AtcSmem sm{s_q, s_kv, s_xbox, q_full, q_empty, kv_full, kv_empty, kv_bytes};
+    const AtcSmem sm{s_q, s_kv, s_xbox, q_full, q_empty, k_full, k_empty, v_full, v_empty, kv_bytes};
     if (warp == 0) {
         if (elect_one()) atc_producer(tmap_q, tmap_kv, tmap_x, p, sm);
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 11) {
         if (elect_one()) {
-            // ===== MMA issuer =====
+            // ===== MMA issuers: one thread per TMEM buffer (warp 1: buffer 0, warp 11: buffer 1) =====
+            // Buffer b carries the units b, b + 2, ...:  Q K^T -> [softmax] -> P.V in nparts pieces -> [drain].  Each thread
+            // blocks only on ITS buffer's barriers, so a group never waits behind the other group's hand-offs (round 1's
+            // single in-order thread: ~1.9 k idle cycles per unit, profiles/r02_attention_trace.txt), and the hardware-assisted
+            // try_wait wakes it ~60 cycles after the arrive (polling both buffers with test_wait from one thread cost ~150
+            // cycles per probe and was slower than the in-order loop).  The tensor core executes the two streams in the order
+            // it receives them; every dependency between them goes through a barrier: the shared O tile (s_free of the other
+            // group), the K / V stages (k_empty / v_empty count one commit per unit of the item).
+            const int buf = warp == 1 ? 0 : 1;
             const int my_items = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
             const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
             const uint32_t idesc_qk = make_idesc_f16(128, static_cast<uint32_t>(p.keys_pad));
             const uint32_t idesc_pv = make_idesc_f16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
             const int ksteps = p.keys_pad >> 4;
+            const uint32_t a_tmem = tmem_base + buf * buf_stride;                     // S, then P, of this buffer
+            const uint32_t o_tmem = shared_o ? tmem_base + 2 * buf_stride : a_tmem + 128;
             auto issue_qk = [&](uint32_t v) {
                 const uint32_t iv = atc_unit_item(v, upi);                      // CTA-local item index of unit v
-                const int kvs = iv & 1, qs = v % kAtcQStages, buf = v & 1;
-                mbar_wait(&kv_full[kvs], (iv >> 1) & 1);
+                const int kvs = iv & 1, qs = v % kAtcQStages;
+                mbar_wait(&k_full[kvs], (iv >> 1) & 1);
                 mbar_wait(&q_full[qs], (v / kAtcQStages) & 1);
                 tcgen05_fence_after();
                 const uint64_t adesc = make_smem_desc_sw128(smem_u32(s_q + qs * kAtcQBytes), 16, 1024);
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes), 16, 1024);
-                const uint32_t d = tmem_base + buf * buf_stride;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+                for (int k = 0; k < 4; ++k) umma_f16(a_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
                 umma_commit(&q_empty[qs]);
                 umma_commit(&s_full[buf]);
+                umma_commit(&k_empty[kvs]);               // this unit is done with the item's K tile
                 ATC_TRACE(0, v, 0);                       // QK^T of unit v issued
             };
-            if (n_units > 0) issue_qk(0);
-            if (n_units > 1) issue_qk(1);
-            for (uint32_t u = 0; u < n_units; ++u) {
-                const int buf = u & 1;
+            if (static_cast<uint32_t>(buf) < n_units) issue_qk(buf);
+            for (uint32_t u = buf; u < n_units; u += 2) {
                 const uint32_t iu = atc_unit_item(u, upi);
                 const int kvs = iu & 1;
-                mbar_wait(&p_full[buf], (u >> 1) & 1);
-                ATC_TRACE(0, u, 1);                       // P of unit u ready
-                tcgen05_fence_after();
                 // V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
                 const uint64_t vdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes + kv_bytes), 1024, 1024);
-                if (shared_o && u >= 1) {     // the shared O tile: drained by the previous unit's group?
-                    mbar_wait(&s_free[buf ^ 1], ((u - 1) >> 1) & 1);
-                    ATC_TRACE(0, u - 1, 3);
+                for (int part = 0; part < nparts; ++part) {
+                    if (part == 0) {
+                        if (shared_o && u >= 1) mbar_wait(&s_free[buf ^ 1], ((u - 1) >> 1) & 1);   // the O tile: drained by unit u - 1's group
+                        mbar_wait(&v_full[kvs], (iu >> 1) & 1);
+                    }
+                    mbar_wait(&p_part[3 * buf + part], (u >> 1) & 1);
+                    if (part == 0) ATC_TRACE(0, u, 1);            // first keys of P of unit u ready
                     tcgen05_fence_after();
+                    const int k0 = 4 * part, k1 = part + 1 == nparts ? ksteps : 4 * (part + 1);
+                    for (int k = k0; k < k1; ++k) umma_f16_ts(o_tmem, a_tmem + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
                 }
-                const uint32_t a = tmem_base + buf * buf_stride;
-                const uint32_t d = shared_o ? tmem_base + 2 * buf_stride : a + 128;
-                for (int k = 0; k < ksteps; ++k) umma_f16_ts(d, a + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
                 umma_commit(&o_full[buf]);
+                umma_commit(&v_empty[kvs]);               // this unit is done with the item's V tile
                 ATC_TRACE(0, u, 2);                       // P.V of unit u issued
-                if (atc_last_unit_of_item(u, upi)) umma_commit(&kv_empty[kvs]);   // last unit of the item: K / V stage reusable
                 if (u + 2 < n_units) {
                     if (!shared_o) {      // O lives inside the score buffer: wait for the drain
                         mbar_wait(&s_free[buf], (u >> 1) & 1);
-                        ATC_TRACE(0, u, 3);                   // buffer of unit u drained
+                        ATC_TRACE(0, u, 3);
                         tcgen05_fence_after();
                     }
-                    issue_qk(u + 2);      // the tensor core runs it behind P.V(u), which is the last reader of P(u)
+                    issue_qk(u + 2);      // the tensor core runs it behind P.V(u) of this thread, the last reader of P(u)
                 }
             }
         }
@@ -611,7 +669,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         // finished its first one, so from then on one group is in the MUFU-bound softmax while the tensor
         // core serves the other group's P.V / next QK^T (the MMA warp issues in exactly that order).
 #ifndef MCM_ATC_NO_STAGGER
-        if (g == 1 && n_units > 1) mbar_wait(&p_full[0], 0);
+        if (g == 1 && n_units > 1) mbar_wait(&p_part[nparts - 1], 0);
 #endif
         for (uint32_t u = g; u < n_units; u += 2) {
             const uint32_t j = u >> 1;
@@ -631,7 +689,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 // S ready: the MMA thread has seen this unit's Q tile and the item's K / V stage land; observing the
                 // same (completed) phases here makes the TMA writes visible to this warp
                 mbar_wait(&q_full[u % kAtcQStages], (u / kAtcQStages) & 1);
-                mbar_wait(&kv_full[iu & 1], (iu >> 1) & 1);
+                mbar_wait(&v_full[iu & 1], (iu >> 1) & 1);
                 if (warp_valid)
                     s_x = atc_dot64(smem_u32(s_q + (u % kAtcQStages) * kAtcQBytes) + (quad * 32 + lane) * 128, lane & 7, sx + 1024);
                 __syncwarp();
@@ -642,7 +700,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             float row_sum = 1.f;
             if (warp_valid) {
                 if (p.n_extra == 0) s_x = -INFINITY;
-                row_sum = atc_two_pass<NFULL, REM16>(t_sr, t_pw, nfull, rem16, S_tc, c, s_x);
+                row_sum = atc_two_pass<NFULL, REM16>(t_sr, t_pw, nfull, rem16, S_tc, c, s_x, &p_part[3 * g], nparts, lane);
                 if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 1);   // both passes issued
                 if (pair) {     // probability 0 for the 64 keys of the other item (for half 0 these columns held this row's
                                 // own scores 32..63: consumed by now)
@@ -657,7 +715,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tcgen05_fence_before();
             __syncwarp();
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 2);       // pass 2 done
-            if (lane == 0) mbar_arrive(&p_full[g]);
+            if (lane == 0) {
+                if (!warp_valid)      // a warp without rows still owes the barriers of the earlier parts its arrival
+                    for (int i = 0; i + 1 < nparts; ++i) mbar_arrive(&p_part[3 * g + i]);
+                mbar_arrive(&p_part[3 * g + nparts - 1]);
+            }
 
             // ---- O = P V is computed by the tensor core; scale by 1 / rowsum and store ----
             mbar_wait(&o_full[g], j & 1);
@@ -704,7 +766,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 4);       // O drained
             if (lane == 0) {
                 mbar_arrive(&s_free[g]);                            // TMEM buffer may be overwritten by the next QK^T
-                if (p.n_extra > 0) mbar_arrive(&kv_empty[iu & 1]);  // this warp is done with the x box of the K / V stage
+                if (p.n_extra > 0) mbar_arrive(&v_empty[iu & 1]);   // this warp is done with the x box of the V stage
                 // 32 rows x 64 head dims of (image, head) leave as ONE bulk store; the output map is 3-D ([image][token][D]),
                 // so rows beyond the image's S tokens (padded query rows) are clipped by the TMA unit
                 if (warp_valid) {
@@ -727,363 +789,5 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
 }
 
-
-// =====================================================================================================================
-// Cooperative softmax (round 2): ALL eight softmax warps work on the SAME unit, then move to the next one.
-//
-// What the phase trace of the kernel above showed (profiles/r02_attention_trace.txt): with one 4-warp group per TMEM
-// buffer, a group idles for ~3.5 k cycles per unit behind its own hand-off chain (P ready -> P.V -> O ready -> drain ->
-// next Q K^T -> S ready, stretched by the in-order MMA thread serving the other group), its softmax passes take 4.3 k
-// because a lone warp per SM sub-partition keeps the MUFU only ~55 % busy, and the two groups drift into phase instead
-// of alternating: 7.8 k cycles per group and unit, 3.85 k per unit.  Here warp (quad, half) owns the 32 rows of TMEM
-// lane quadrant `quad` and one HALF of the key columns, so every sub-partition runs two warps of the same pass (the
-// MUFU saturates: the exp2 pass of a unit takes ~1.9 k instead of 3.1 k), and the hand-off chain of one buffer hides
-// completely behind the softmax of the other:
-//      wait S(u) | row max over own columns, exchange with the partner warp (shared memory + a 64-thread barrier)
-//                | drain O(u-1)  (P.V(u-1) was issued when pass 2 of unit u-1 ended)   -> frees buffer (u-1) & 1, the
-//                |                                                                       MMA thread issues Q K^T(u+1) into it
-//                | exp2 pass over own columns, P in place                              -> MMA thread issues P.V(u)
-// TMEM map of buffer b (base = b * 256), h0 / h1 = key columns of half 0 / half 1 (multiples of 16):
-//      S fp32 [0, keys_pad)    P fp16: half 0 -> [0, h0/2), half 1 -> [h0, h0 + h1/2)  (each behind its own read pointer)
-//      O fp32 [o_col, o_col + 64): 64 if h0 >= 128 (between the two P halves), else the next multiple of 32 behind P of half 1
-// =====================================================================================================================
-struct AtcSplit {
-    int g0, h0, h1, o_col;
-};
-__host__ __device__ inline AtcSplit atc_split(int keys_pad) {
-    AtcSplit c;
-    const int groups = keys_pad >> 4;
-    c.g0 = groups > 1 ? groups >> 1 : 1;     // odd counts: the 16-column remainder chunk (and with it the padded keys) goes to half 1
-    c.h0 = c.g0 << 4;
-    c.h1 = keys_pad - c.h0;
-    c.o_col = c.h0 >= 128 ? 64 : ((c.h0 + (c.h1 >> 1) + 31) & ~31);
-    return c;
-}
-constexpr int kAtcXchBytes = 2 * 2 * 128 * 16;     // [unit parity][half][row] float4 {partial max, partial sum, p_extra, -}
-
-__host__ __device__ inline int atc_coop_smem_bytes(int keys_pad) {
-    return kAtcQStages * kAtcQBytes + 2 * 2 * keys_pad * 128 + 2 * kAtcXBytes + 8 * 2048 /*O staging*/ + kAtcXchBytes + 1024 /*barriers*/ +
-           1024 /*align*/;
-}
-
-__device__ __forceinline__ void bar_sync_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-
-__global__ void __launch_bounds__(kAtcThreads, 1)
-attention_coop_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                      const __grid_constant__ CUtensorMap tmap_x, const AtcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int kv_bytes = p.keys_pad * 128;                       // one K or V tile
-    uint8_t* s_q = smem;                                         // [kAtcQStages][16 KB]
-    uint8_t* s_kv = smem + kAtcQStages * kAtcQBytes;             // [2][K | V]
-    uint8_t* s_xbox = s_kv + 4 * kv_bytes;                       // [2][q | k | v of tokens 256..263]  (S > 256 only)
-    uint8_t* s_stage = s_xbox + 2 * kAtcXBytes;                  // [8 warps][32 rows][64 B]
-    float4* s_xch = reinterpret_cast<float4*>(s_stage + 8 * 2048);   // [2][2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_xch) + kAtcXchBytes);
-    uint64_t* q_full = bars;                       // [3]
-    uint64_t* q_empty = bars + kAtcQStages;        // [3]
-    uint64_t* kv_full = bars + 2 * kAtcQStages;    // [2]
-    uint64_t* kv_empty = kv_full + 2;              // [2]
-    uint64_t* s_full = kv_full + 4;                // [2]  MMA -> softmax warps: S ready
-    uint64_t* p_full = kv_full + 6;                // [2]  softmax warps -> MMA: P written
-    uint64_t* o_full = kv_full + 8;                // [2]  MMA -> softmax warps: O ready
-    uint64_t* s_free = kv_full + 10;               // [2]  softmax warps -> MMA: O drained, buffer reusable
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(kv_full + 12);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n_items = p.b * p.H;
-    const bool pair = p.pair_mode != 0;
-    const int n_work = pair ? (n_items + 1) / 2 : n_items;
-    const int upi = p.units_per_item;
-    const int D = p.H * 64;
-    const AtcSplit sp = atc_split(p.keys_pad);
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_kv);
-        if (p.n_extra > 0) tma_prefetch_desc(&tmap_x);
-        // with an extra key the half-1 softmax warps read their q rows from the Q tile (4 arrivals per unit) and all
-        // eight read v of the extra token from the x box while draining O (8 arrivals per unit)
-        for (int i = 0; i < kAtcQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], p.n_extra > 0 ? 5 : 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], p.n_extra > 0 ? 2 + 8 * upi : 1);
-            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8);
-            mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 8);
-        }
-        fence_barrier_init();
-    }
-    pdl_launch_dependents();
-    if (warp == 1) tmem_alloc<512>(tmem_ptr);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    pdl_wait();
-
-    const AtcSmem sm{s_q, s_kv, s_xbox, q_full, q_empty, kv_full, kv_empty, kv_bytes};
-    const int my_items = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const uint32_t n_units = my_items > 0 ? static_cast<uint32_t>(my_items * upi) : 0u;
-    if (warp == 0) {
-        if (elect_one()) atc_producer(tmap_q, tmap_kv, tmap_x, p, sm);
-    } else if (warp == 1) {
-        if (elect_one()) {
-            // ===== MMA issuer =====
-            const uint32_t idesc_qk = make_idesc_f16(128, static_cast<uint32_t>(p.keys_pad));
-            const uint32_t idesc_pv = make_idesc_f16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
-            const int ksteps = p.keys_pad >> 4;
-            auto issue_qk = [&](uint32_t v) {
-                const uint32_t iv = atc_unit_item(v, upi);                      // CTA-local item index of unit v
-                const int kvs = iv & 1, qs = v % kAtcQStages, buf = v & 1;
-                mbar_wait(&kv_full[kvs], (iv >> 1) & 1);
-                mbar_wait(&q_full[qs], (v / kAtcQStages) & 1);
-                tcgen05_fence_after();
-                const uint64_t adesc = make_smem_desc_sw128(smem_u32(s_q + qs * kAtcQBytes), 16, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes), 16, 1024);
-                const uint32_t d = tmem_base + buf * 256;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
-                umma_commit(&q_empty[qs]);
-                umma_commit(&s_full[buf]);
-                ATC_TRACE(0, v, 0);                       // QK^T of unit v issued
-            };
-            if (n_units > 0) issue_qk(0);
-            if (n_units > 1) issue_qk(1);
-            for (uint32_t u = 0; u < n_units; ++u) {
-                const int buf = u & 1;
-                if (u >= 1 && u + 1 < n_units) {
-                    // O(u-1) drained (the softmax warps do that right after the row-max pass of unit u): its buffer takes S(u+1)
-                    mbar_wait(&s_free[buf ^ 1], ((u - 1) >> 1) & 1);
-                    ATC_TRACE(0, u - 1, 3);
-                    tcgen05_fence_after();
-                    issue_qk(u + 1);
-                }
-                const uint32_t iu = atc_unit_item(u, upi);
-                const int kvs = iu & 1;
-                mbar_wait(&p_full[buf], (u >> 1) & 1);
-                ATC_TRACE(0, u, 1);                       // P of unit u ready
-                tcgen05_fence_after();
-                // V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
-                const uint64_t vdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes + kv_bytes), 1024, 1024);
-                const uint32_t base = tmem_base + buf * 256;
-                const uint32_t d = base + sp.o_col;
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t a = base + (k < sp.g0 ? 8 * k : sp.h0 + 8 * (k - sp.g0));
-                    umma_f16_ts(d, a, vdesc + 128ull * k, idesc_pv, k != 0);
-                }
-                umma_commit(&o_full[buf]);
-                ATC_TRACE(0, u, 2);                       // P.V of unit u issued
-                if (atc_last_unit_of_item(u, upi)) umma_commit(&kv_empty[kvs]);   // last unit of the item: K / V stage reusable
-            }
-        }
-    } else if (warp == 10) {
-        if (p.n_extra > 0) atc_tail_rows(p, sm, lane);
-    } else {
-        // ===== softmax / epilogue warps: warp (quad, half) = rows of TMEM lane quadrant `quad`, key columns of `half` =====
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t stg = smem_u32(s_stage + (warp - 2) * 2048);       // this warp's staging tile: 32 rows x 64 B
-        const float c = p.scale_log2e;
-        const int S_tc = p.S - p.n_extra;            // keys that go through the tensor core
-        const int col_lo = half ? sp.h0 : 0;         // first S column (= key index) of this warp; its P starts at the same column
-        const int ncols = half ? sp.h1 : sp.h0;
-        // pair mode: rows of quads 0, 1 belong to item 0 of the pair (keys 0..63), quads 2, 3 to item 1 (keys 64..127);
-        // h0 = h1 = 64, so a warp either owns its item's keys (half == own item) or the other item's (probability 0)
-        const int pitem = pair ? (quad >> 1) : 0;
-        const bool own_keys = !pair || half == pitem;
-        const int key0 = pair ? 0 : col_lo;          // key index of this warp's first column within its item
-        const int nfull = ncols >> 5;
-        const bool rem16 = (ncols & 16) != 0;
-        const int row_t = quad * 32 + lane;          // row of the 128-row unit tile
-        // explicit shared-space accesses (a pointer carved out of the dynamic buffer compiles to generic LD / ST)
-        const uint32_t xch_mine = smem_u32(s_xch) + (half * 128 + row_t) * 16;
-        const uint32_t xch_other = smem_u32(s_xch) + ((half ^ 1) * 128 + row_t) * 16;
-
-        // drain O of unit v: this warp's 32 head dims (half) of its 32 rows -> fp16 -> staging -> coalesced 64-byte row pieces
-        auto drain = [&](uint32_t v) {
-            const int vbuf = v & 1, vpar = (v >> 1) & 1;
-            const uint32_t iv = atc_unit_item(v, upi);
-            const int mt = static_cast<int>(v - iv * upi);
-            const int work = static_cast<int>(blockIdx.x) + static_cast<int>(iv) * static_cast<int>(gridDim.x);
-            const int item = pair ? 2 * work + pitem : work;
-            const int img = atc_div_h(item, p.inv_H), h = item - img * p.H;
-            const int wrow0 = pair ? (quad & 1) * 32 : mt * 128 + quad * 32;
-            const bool valid = item < n_items && wrow0 < p.S;
-            mbar_wait(&o_full[vbuf], vpar);
-            if (quad == 2 && lane == 0) ATC_TRACE(1 + half, v, 3);       // O ready
-            tcgen05_fence_after();
-            if (valid) {
-                const uint32_t xo = static_cast<uint32_t>(vbuf) * 2 * 128 * 16;          // exchange slots of unit parity v & 1
-                const float4 a = lds_v4(xch_mine + xo), b = lds_v4(xch_other + xo);
-                const float inv = 1.0f / (a.y + b.y);
-                uint32_t o[32];
-                tmem_ld_32x32b_x32(tmem_base + t_lane + vbuf * 256 + sp.o_col + half * 32, o);
-                tmem_ld_wait();
-                if (p.n_extra > 0) {   // O += p_extra * v_extra (warp-uniform addresses: broadcast loads)
-                    const float px = half ? a.z : b.z;
-                    const uint32_t sx = smem_u32(s_xbox + (iv & 1) * kAtcXBytes);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint4 w = lds_v4u(sx + 2048 + ((half * 4 + q) << 4));
-                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = unpack_op16x2(ws[e]);
-                            o[8 * q + 2 * e] = __float_as_uint(fmaf(px, f.x, __uint_as_float(o[8 * q + 2 * e])));
-                            o[8 * q + 2 * e + 1] = __float_as_uint(fmaf(px, f.y, __uint_as_float(o[8 * q + 2 * e + 1])));
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {     // 4 x 16-byte chunks (8 fp16) of this row's 32 head dims
-                    uint4 w;
-                    w.x = pack_op16x2(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-                    w.y = pack_op16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-                    w.z = pack_op16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-                    w.w = pack_op16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-                    sts_v4u(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), w);
-                }
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (quad == 2 && lane == 0) ATC_TRACE(1 + half, v, 4);       // O drained
-            if (lane == 0) {
-                mbar_arrive(&s_free[vbuf]);                           // the buffer may take the next S
-                if (p.n_extra > 0) mbar_arrive(&kv_empty[iv & 1]);    // this warp is done with the x box of the K / V stage
-            }
-            if (valid) {
-                const int cq = lane & 3;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = (lane >> 2) + 8 * i;
-                    const int row = wrow0 + r;
-                    if (row < p.S) {
-                        const uint4 w = lds_v4u(stg + r * 64 + ((cq ^ ((r >> 1) & 3)) << 4));
-                        *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(img) * p.S + row) * D + h * 64 + half * 32 + cq * 8) = w;
-                    }
-                }
-            }
-            __syncwarp();
-        };
-
-        for (uint32_t u = 0; u < n_units; ++u) {
-            const int buf = u & 1;
-            const uint32_t j = u >> 1;
-            const uint32_t iu = atc_unit_item(u, upi);
-            const int mt = static_cast<int>(u - iu * upi);
-            const int work = static_cast<int>(blockIdx.x) + static_cast<int>(iu) * static_cast<int>(gridDim.x);
-            const int item = pair ? 2 * work + pitem : work;
-            const int wrow0 = pair ? (quad & 1) * 32 : mt * 128 + quad * 32;
-            const bool warp_valid = item < n_items && wrow0 < p.S;
-            const uint32_t t_s = tmem_base + t_lane + buf * 256 + col_lo;      // first S column of this warp (its P starts here too)
-            const uint32_t xo = static_cast<uint32_t>(buf) * 2 * 128 * 16;
-            float s_x = -INFINITY;
-            const uint32_t sx = smem_u32(s_xbox + (iu & 1) * kAtcXBytes);
-
-            mbar_wait(&s_full[buf], j & 1);
-            if (p.n_extra > 0 && half == 1) {
-                // the extra key (ViT-L/14's 257th token): this row's raw score against it, on the CUDA cores (half-1 warps).
-                // S ready => the MMA thread has seen this unit's Q tile and the item's K / V stage land; observing the same
-                // (completed) phases here makes the TMA writes visible to this warp
-                mbar_wait(&q_full[u % kAtcQStages], (u / kAtcQStages) & 1);
-                mbar_wait(&kv_full[iu & 1], (iu >> 1) & 1);
-                if (warp_valid)
-                    s_x = atc_dot64(smem_u32(s_q + (u % kAtcQStages) * kAtcQBytes) + (quad * 32 + lane) * 128, lane & 7, sx + 1024);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&q_empty[u % kAtcQStages]);
-            }
-            if (quad == 2 && lane == 0) ATC_TRACE(1 + half, u, 0);       // S ready
-            tcgen05_fence_after();
-
-            // ---- pass 1: partial row max over this warp's key columns ----
-            float mx = s_x;
-            if (warp_valid && own_keys) {
-                for (int ch = 0; ch < nfull; ch += 2) {
-                    uint32_t va[32], vb[32];
-                    const bool two = ch + 1 < nfull;
-                    tmem_ld_32x32b_x32(t_s + ch * 32, va);
-                    if (two) tmem_ld_32x32b_x32(t_s + ch * 32 + 32, vb);
-                    tmem_ld_wait();
-                    mx = atc_chunk_max(va, key0 + ch * 32, S_tc, mx);
-                    if (two) mx = atc_chunk_max(vb, key0 + ch * 32 + 32, S_tc, mx);
-                }
-                if (rem16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_s + nfull * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (key0 + nfull * 32 + e < S_tc) mx = fmaxf(mx, __uint_as_float(v[e]));
-                }
-            }
-            sts_v4(xch_mine + xo, make_float4(mx, 0.f, 0.f, 0.f));
-            bar_sync_named(1 + quad, 64);            // the two warps that share these 32 rows
-            const float mc = fmaxf(mx, lds_v4(xch_other + xo).x) * c;
-            if (quad == 2 && lane == 0) ATC_TRACE(1 + half, u, 1);   // pass 1 done
-
-            // ---- O of the previous unit: its P.V was issued when that unit's pass 2 ended ----
-            if (u > 0) drain(u - 1);
-
-            // ---- pass 2: p = 2^(s * c - max * c); P (fp16) goes over the first half of this warp's own S columns ----
-            float sum0 = 0.f, sum1 = 0.f, px = 0.f;
-            if (warp_valid) {
-                if (own_keys) {
-                    for (int ch = 0; ch < nfull; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(t_s + ch * 32, v);
-                        tmem_ld_wait();
-                        atc_chunk_exp(v, key0 + ch * 32, S_tc, c, mc, sum0, sum1, t_s + ch * 16);
-                    }
-                    if (rem16) {
-                        uint32_t v[16];
-                        tmem_ld_32x32b_x16(t_s + nfull * 32, v);
-                        tmem_ld_wait();
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int k0 = key0 + nfull * 32 + 2 * e;
-                            const float p0 = (k0 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc)) : 0.f;
-                            const float p1 = (k0 + 1 < S_tc) ? ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc)) : 0.f;
-                            sum0 += p0;
-                            sum1 += p1;
-                            pk[e] = pack_op16x2(p0, p1);
-                        }
-                        tmem_st_32x32b_x8(t_s + nfull * 16, pk);
-                    }
-                    if (p.n_extra > 0 && half == 1) {   // probability of the extra key, rounded like the P operand
-                        const float pe = ex2_approx(fmaf(s_x, c, -mc));
-                        sum0 += pe;
-                        px = unpack_op16x2(pack_op16x2(pe, 0.f)).x;
-                    }
-                } else {      // pair mode: this warp's columns are the OTHER item's keys: probability 0
-                    uint32_t zero[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) zero[e] = 0u;
-                    for (int i = 0; i < (ncols >> 5); ++i) tmem_st_32x32b_x16(t_s + 16 * i, zero);
-                }
-                tmem_st_wait();
-            }
-            sts_v4(xch_mine + xo, make_float4(mx, sum0 + sum1, px, 0.f));
-            tcgen05_fence_before();
-            __syncwarp();
-            if (quad == 2 && lane == 0) ATC_TRACE(1 + half, u, 2);       // pass 2 done
-            if (lane == 0) mbar_arrive(&p_full[buf]);
-        }
-        if (n_units > 0) {
-            bar_sync_named(1 + quad, 64);        // the partner's sums of the last unit (no later row-max exchange orders them)
-            drain(n_units - 1);
-        }
-    }
-
-    __syncwarp();
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
 
 }  // namespace mcm

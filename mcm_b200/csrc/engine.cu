@@ -116,7 +116,6 @@ struct McmHandle {
     CUtensorMap tm_patches_lo, tm_xh_lo, tm_attn_lo, tm_hid_lo;
     CUtensorMap tm_qkv_q, tm_qkv_kv, tm_qkv_x, tm_attn_o;   // attention: 128-row Q boxes / keys_pad-row K,V boxes / 8-row boxes (tokens >= 256) over the fused QKV buffer
     bool attn_mma = false;             // debug A/B switch (env MCM_ATTN_MMA=1): warp-level mma.sync attention
-    bool attn_v1 = true;               // MCM_OPT_ATTENTION_V1: the round-1 kernel (one softmax group per TMEM buffer)
     bool cls_shortcut = true;
 
     // uint8 ingest: Normalize constants of the reference preprocess (utils/train_eval_util.py:27-28)
@@ -619,19 +618,15 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
     const int items = p.pair_mode ? (b * H + 1) / 2 : b * H;
     const int grid = items < h->num_sms ? items : h->num_sms;
     ProfScope prof(h, MCM_PROF_ATTENTION, st);
-    if (h->attn_v1) {
+    {
         const int smem = atc_smem_bytes(p.keys_pad);
-        // softmax passes unrolled for the two production shapes (attention_tcgen05.cuh, atc_two_pass)
+        // softmax passes with constant trip counts for the two production shapes (attention_tcgen05.cuh, atc_two_pass)
         auto kern = attention_tcgen05_kernel<-1, false>;
         const int s_tc = S - p.n_extra;
         if (!p.pair_mode && p.keys_pad == 208 && s_tc >= 192) kern = attention_tcgen05_kernel<6, true>;
         else if (!p.pair_mode && p.keys_pad == 256 && s_tc >= 256) kern = attention_tcgen05_kernel<8, false>;
         MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(kern), smem));
         MCM_CUDA(h, launch_k(kern, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, to, p));
-    } else {
-        const int smem = atc_coop_smem_bytes(p.keys_pad);
-        MCM_CUDA(h, ensure_smem(h, reinterpret_cast<const void*>(attention_coop_kernel), smem));
-        MCM_CUDA(h, launch_k(attention_coop_kernel, dim3(grid), dim3(kAtcThreads), smem, st, 1, tq, tkv, tx, p));
     }
 #ifdef MCM_ATC_TRACE
     {
@@ -1573,7 +1568,6 @@ int mcm_set_option(McmHandle* h, int32_t option, int32_t value) {
     switch (option) {
         case MCM_OPT_CLS_SHORTCUT: h->cls_shortcut = value != 0; return MCM_OK;
         case MCM_OPT_CUDA_GRAPH: h->use_graph = value != 0; return MCM_OK;
-        case MCM_OPT_ATTENTION_V1: h->attn_v1 = value != 0; return MCM_OK;
         case MCM_OPT_PRECISION: {
             if (value != MCM_PRECISION_FP16 && value != MCM_PRECISION_SPLIT) return fail(h, MCM_EINVAL, "unknown precision mode %d", value);
             if (value == MCM_PRECISION_SPLIT && !h->hid_lo) {

@@ -456,10 +456,6 @@ class McmEngine:
         """Replay the forward from a CUDA graph captured per (input buffer, batch size, options): small batches."""
         self._check(self._lib.mcm_set_option(self._h, _lib.OPT_CUDA_GRAPH, 1 if on else 0))
 
-    def set_attention_v1(self, on: bool) -> None:
-        """A/B measurements: the round-1 attention kernel instead of the cooperative one (same results)."""
-        self._check(self._lib.mcm_set_option(self._h, _lib.OPT_ATTENTION_V1, 1 if on else 0))
-
     def allgather_scores(self, nccl_comm: int, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """``mcm_allgather_scores``: one NCCL all-gather of this rank's (padded) score vector on the current stream;
         ``nccl_comm`` is a raw ``ncclComm_t`` (see :class:`mcm_b200.parallel.NcclComm`)."""
