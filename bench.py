@@ -435,7 +435,7 @@ def main():
                        "l2": f"resident input pool {len(pool)} x {B * 3 * 224 * 224 * 4 / 1e6:.0f} MB rotates (> 126 MB L2)",
                        "precision": "fp16 tensor-core operands, fp32 accumulation / LayerNorm statistics / softmax / tail, residual "
                                     "stream as an fp16 (hi, lo) pair; precision_split = every operand an fp16 pair",
-                       "cpu_affinity": (f"{len(cpus)} cores of the GPU's NUMA node" if cpus else "unpinned (topology not readable)")},
+                       "cpu_affinity": (f"{len(cpus)} cores of the GPU's NUMA node" if cpus else "unpinned (sysfs and NVML give no narrower CPU set for this GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
                     "d2h_bytes_per_step": B * 4},
             "e2e_uint8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2,

@@ -182,20 +182,48 @@ __device__ __forceinline__ float atc_chunk_max(const uint32_t (&v)[32], int k0, 
     }
     return mx;
 }
+// 2^x for x <= 0 WITHOUT the special-function unit: round-to-nearest split x = j + f (the magic-number add leaves j in the
+// low mantissa bits of r), a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (relative error 7.5e-5, a sixth of the
+// fp16 rounding the probability gets next), and j added into the exponent field.  8 FMA/ALU-pipe instructions against ONE
+// MUFU.EX2 -- but the SM has 16 MUFU lanes per clock against 128 FMA lanes, and the exp2 pass of a softmax warp is paced by
+// its own back-to-back MUFU instructions (8 cycles each per warp); these fill the issue slots in between.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.f);                                   // keeps the exponent field positive; 2^-125 rounds to P = 0 anyway
+    const float r = x + 12582912.f;                         // 1.5 * 2^23
+    const float f = x - (r - 12582912.f);
+    float p = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+// which of the 32 keys of a full chunk take ex2_poly instead of MUFU.EX2 (bit i = key i of the chunk)
+#ifndef MCM_ATC_POLY_MASK
+#define MCM_ATC_POLY_MASK 0x88888888u
+#endif
+template <int I>
+__device__ __forceinline__ float atc_ex2(float x) {
+    if constexpr (((MCM_ATC_POLY_MASK >> I) & 1u) != 0) return ex2_poly(x);
+    else return ex2_approx(x);
+}
+template <int E>
+__device__ __forceinline__ void atc_exp_pairs(const uint32_t (&v)[32], float c, float mc, float& sum0, float& sum1, uint32_t (&pk)[16]) {
+    if constexpr (E < 16) {
+        const float p0 = atc_ex2<2 * E>(fmaf(__uint_as_float(v[2 * E]), c, -mc));
+        const float p1 = atc_ex2<2 * E + 1>(fmaf(__uint_as_float(v[2 * E + 1]), c, -mc));
+        sum0 += p0;
+        sum1 += p1;
+        pk[E] = pack_op16x2(p0, p1);
+        atc_exp_pairs<E + 1>(v, c, mc, sum0, sum1, pk);
+    }
+}
+
 // p = 2^(s * c - mc) for one 32-key chunk, accumulated into two partial row sums and written to TMEM
 // as 16 packed fp16 pairs (the A operand of P.V) at `t_p`
 __device__ __forceinline__ void atc_chunk_exp(const uint32_t (&v)[32], int k0, int S, float c, float mc, float& sum0,
                                               float& sum1, uint32_t t_p) {
     uint32_t pk[16];
     if (k0 + 32 <= S) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc));
-            sum0 += p0;
-            sum1 += p1;
-            pk[e] = pack_op16x2(p0, p1);
-        }
+        atc_exp_pairs<0>(v, c, mc, sum0, sum1, pk);
     } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -224,9 +252,13 @@ __device__ __forceinline__ void atc_chunk_exp(const uint32_t (&v)[32], int k0, i
 // phase per unit: arrivals carry no phase tag, so a fast warp signalling part p + 1 on a single multi-phase barrier before its
 // neighbours signalled part p would be counted towards part p (that deadlocked the first version).  atc_parts() is the split
 // both sides agree on.
+#ifndef MCM_ATC_MAX_PARTS
+#define MCM_ATC_MAX_PARTS 3
+#endif
+constexpr int kAtcMaxParts = MCM_ATC_MAX_PARTS;
 __host__ __device__ inline int atc_parts(int keys_pad, int pair_mode) {
-    const int n4 = (keys_pad >> 4) >> 2;          // whole groups of 4 k-steps
-    return pair_mode ? 1 : (n4 < 1 ? 1 : (n4 > 3 ? 3 : n4));
+    const int n4 = ((keys_pad >> 4) + 3) >> 2;    // groups of 4 k-steps, the last one possibly short
+    return pair_mode ? 1 : (n4 > kAtcMaxParts ? kAtcMaxParts : n4);
 }
 __device__ __forceinline__ void atc_signal_part(uint64_t* p_part, int lane) {
     tmem_st_wait();
@@ -270,6 +302,7 @@ __device__ __forceinline__ float atc_two_pass(uint32_t t_sr, uint32_t t_pw, int 
         atc_chunk_exp(v, ch * 32, s_lim, c, mc, sum0, sum1, t_pw + ch * 16);
         if (ch == 1 && nparts > 1) atc_signal_part(p_part, lane);          // keys 0..63 are final
         if (ch == 3 && nparts > 2) atc_signal_part(p_part + 1, lane);      // keys 64..127 are final
+        if (kAtcMaxParts > 3 && ch == 5 && nparts > 3) atc_signal_part(p_part + 2, lane);   // keys 128..191
     }
     if (rem16) {
         uint32_t v[16];
@@ -530,8 +563,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     uint64_t* s_full = k_full + 8;                 // [2]  MMA -> softmax group: S ready
     uint64_t* o_full = k_full + 10;                // [2]  MMA -> softmax group: O ready
     uint64_t* s_free = k_full + 12;                // [2]  softmax group -> MMA: O drained
-    uint64_t* p_part = k_full + 14;                // [2][3]  softmax group -> MMA: part p (64 keys) of P written
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(k_full + 20);
+    uint64_t* p_part = k_full + 14;                // [2][kAtcMaxParts]  softmax group -> MMA: part p (64 keys) of P written
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(k_full + 14 + 2 * kAtcMaxParts);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -566,7 +599,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], upi + (p.n_extra > 0 ? 1 : 0));            // + tail-row warp
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], upi + (p.n_extra > 0 ? 1 + 4 * upi : 0));  // + tail-row warp + 4 softmax warps per unit
             mbar_init(&s_full[i], 1);
-            for (int q = 0; q < 3; ++q) mbar_init(&p_part[3 * i + q], 4);
+            for (int q = 0; q < kAtcMaxParts; ++q) mbar_init(&p_part[kAtcMaxParts * i + q], 4);
             mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
         }
         fence_barrier_init();
@@ -626,7 +659,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         if (shared_o && u >= 1) mbar_wait(&s_free[buf ^ 1], ((u - 1) >> 1) & 1);   // the O tile: drained by unit u - 1's group
                         mbar_wait(&v_full[kvs], (iu >> 1) & 1);
                     }
-                    mbar_wait(&p_part[3 * buf + part], (u >> 1) & 1);
+                    mbar_wait(&p_part[kAtcMaxParts * buf + part], (u >> 1) & 1);
                     if (part == 0) ATC_TRACE(0, u, 1);            // first keys of P of unit u ready
                     tcgen05_fence_after();
                     const int k0 = 4 * part, k1 = part + 1 == nparts ? ksteps : 4 * (part + 1);
@@ -700,7 +733,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             float row_sum = 1.f;
             if (warp_valid) {
                 if (p.n_extra == 0) s_x = -INFINITY;
-                row_sum = atc_two_pass<NFULL, REM16>(t_sr, t_pw, nfull, rem16, S_tc, c, s_x, &p_part[3 * g], nparts, lane);
+                row_sum = atc_two_pass<NFULL, REM16>(t_sr, t_pw, nfull, rem16, S_tc, c, s_x, &p_part[kAtcMaxParts * g], nparts, lane);
                 if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 1);   // both passes issued
                 if (pair) {     // probability 0 for the 64 keys of the other item (for half 0 these columns held this row's
                                 // own scores 32..63: consumed by now)
@@ -717,8 +750,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 2);       // pass 2 done
             if (lane == 0) {
                 if (!warp_valid)      // a warp without rows still owes the barriers of the earlier parts its arrival
-                    for (int i = 0; i + 1 < nparts; ++i) mbar_arrive(&p_part[3 * g + i]);
-                mbar_arrive(&p_part[3 * g + nparts - 1]);
+                    for (int i = 0; i + 1 < nparts; ++i) mbar_arrive(&p_part[kAtcMaxParts * g + i]);
+                mbar_arrive(&p_part[kAtcMaxParts * g + nparts - 1]);
             }
 
             // ---- O = P V is computed by the tensor core; scale by 1 / rowsum and store ----

@@ -33,6 +33,9 @@
 #include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
+#ifndef MCM_RESID_H2_TMA_MAX_K
+#define MCM_RESID_H2_TMA_MAX_K 1024   // residual-pair GEMMs with K up to this take the all-TMA epilogue (A/B builds: 0 or 4096)
+#endif
 #include "resize.cuh"
 #include "rowwise.cuh"
 #include "tail.cuh"
@@ -455,7 +458,7 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
             return fail(h, MCM_EINVAL, "EPI_BIAS_RESID_H2_LN needs the residual pair, the output pair and the statistics buffer");
         // short-K GEMMs (out_proj) are bound by the residual traffic: all of it through TMA; long-K ones hide the LSU epilogue
         // behind the main loop and keep more ring stages; the split mode's k-loop is 3x longer anyway
-        if (!split && ln.resid16 == ln.out16 && ln.resid16_lo == ln.out16_lo && K <= 1024) epi = EPI_BIAS_RESID_H2_LN_TMA;
+        if (!split && ln.resid16 == ln.out16 && ln.resid16_lo == ln.out16_lo && K <= MCM_RESID_H2_TMA_MAX_K) epi = EPI_BIAS_RESID_H2_LN_TMA;
     }
     if (epi == EPI_BIAS_RESID_H2_LN_TMA) {
         int rc = make_tmap_epi(h, &tout, ln.out16, M, N, false, 32);

@@ -40,7 +40,10 @@ constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
 #endif
 constexpr int kResidBufs = MCM_RESID_BUFS;   // TMA residual epilogue: residual chunks in flight per warp
 constexpr int kResidWarpBytes = kResidBufs * 4096 + 2048;   // + the fp16 staging tile
-constexpr int kResidH2Bufs = 3;      // (hi, lo) TMA residual epilogue: 2 KB + 2 KB chunks in flight per warp (two loads ahead)
+#ifndef MCM_RESID_H2_BUFS
+#define MCM_RESID_H2_BUFS 3
+#endif
+constexpr int kResidH2Bufs = MCM_RESID_H2_BUFS;   // (hi, lo) TMA residual epilogue: 2 KB + 2 KB chunks per warp, all but one in flight
 constexpr int kMaxStatsParts = 8;    // LayerNorm fold: partial row statistics per row (width <= 1024: 2 per 256-column tile)
 constexpr int kStgLd = 32;           // fp32 staging row stride in floats; 16-byte chunks are XOR-swizzled by (row & 7)
 
@@ -103,8 +106,20 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of any CTA of the cluster (shared::cluster address).  Default semantics (release at CTA scope): what
+// it orders here is a drained TENSOR-MEMORY stage (tcgen05.wait::ld + tcgen05.fence::before_thread_sync in front of it), never
+// generic-proxy memory.  Round 1 used `.release.cluster`, which ptxas lowers to MEMBAR.ALL.GPU + ERRBAR in front of the
+// arrive: ncu's source view put 23-26 % of ALL warp-stall samples of the q/k/v and fc1 GEMMs (16 epilogue warps, one release
+// per warp and tile) on those three instructions (profiles/r02_ncu_gemm_vit_b16.txt).
+#ifndef MCM_ARRIVE_RELEASE_CLUSTER
+#define MCM_ARRIVE_RELEASE_CLUSTER 0
+#endif
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if MCM_ARRIVE_RELEASE_CLUSTER
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // 2D tiled load into THIS CTA's smem; the byte count is signalled on `bar_cluster_addr`, a
 // shared::cluster mbarrier address that may live in the peer (leader) CTA.

@@ -133,37 +133,58 @@ def gather_scores_nccl(engine, comm: NcclComm, local: torch.Tensor, n: int) -> n
     return recv[:n].cpu().numpy().astype(np.float32, copy=True)
 
 
+def _cpus_from_sysfs(device: int):
+    pr = torch.cuda.get_device_properties(device)
+    if not (hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id")):
+        return None
+    bus = f"{int(getattr(pr, 'pci_domain_id', 0)):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
+    with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+        node = int(f.read().strip())
+    if node < 0:                                   # one NUMA node, or a VM that hides the topology
+        return None
+    with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+        spec = f.read().strip()
+    cpus = []
+    for part in spec.split(","):
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def _cpus_from_nvml(device: int):
+    """NVML's own view of the GPU's ideal CPU set (what ``nvidia-smi topo -m`` prints as CPU Affinity)."""
+    import os
+    import pynvml
+    pynvml.nvmlInit()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    index = device
+    if vis:                                        # torch's ordinal -> NVML's: only plain integer lists are mapped
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if device < len(ids) and ids[device].isdigit():
+            index = int(ids[device])
+    handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+    ncpu = os.cpu_count() or 64
+    words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+    return [w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+
+
 def pin_to_gpu_numa(device: int) -> Optional[list]:
     """Bind this process (one rank per GPU) to the CPU cores of its GPU's NUMA node: the pinned host buffers of the
     end-to-end path are then allocated on, and copied from, the memory next to that GPU's PCIe root, instead of eight
-    ranks pulling pixels through one socket.  Returns the CPU list it bound to, or None when the topology cannot be
-    read (single-socket boxes, containers without sysfs) -- never an error."""
+    ranks pulling pixels through one socket.  The CPU set comes from sysfs (PCI device -> numa_node -> cpulist) or,
+    where a container hides that, from NVML's CPU affinity of the device.  Returns the CPU list it bound to, or None
+    when neither source narrows the current affinity (single-socket boxes) -- never an error."""
     import os
-    try:
-        pr = torch.cuda.get_device_properties(device)
-        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
-            bus = f"{int(getattr(pr, 'pci_domain_id', 0)):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
-        else:
-            import pynvml
-            pynvml.nvmlInit()
-            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
-            bus = (bus.decode() if isinstance(bus, bytes) else str(bus)).lower()
-            if len(bus.split(":")[0]) == 8:            # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
-                bus = bus[4:]
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
+    have = set(os.sched_getaffinity(0))
+    for source in (_cpus_from_sysfs, _cpus_from_nvml):
+        try:
+            cpus = source(device)
+        except Exception:
+            continue
+        allowed = sorted(set(cpus or ()) & have)
+        if allowed and len(allowed) < len(have):
+            os.sched_setaffinity(0, allowed)
+            return allowed
+        if allowed:                                # the device's set IS the whole machine: nothing to narrow
             return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            spec = f.read().strip()
-        cpus = []
-        for part in spec.split(","):
-            a, _, b = part.partition("-")
-            cpus.extend(range(int(a), int(b or a) + 1))
-        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
-        if not allowed:
-            return None
-        os.sched_setaffinity(0, allowed)
-        return allowed
-    except Exception:
-        return None
+    return None

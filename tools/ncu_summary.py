@@ -55,7 +55,7 @@ def full(path):
         print("-" * 100)
         print(row[hdr.index("Kernel Name")])
         for i, h in enumerate(hdr):
-            if h in KEEP or any(h.endswith("." + k) for k in KEEP):
+            if (h in KEEP or any(h.endswith("." + k) for k in KEEP)) and row[i] != "":
                 print(f"  {h.split('TriageCompute.')[-1]:92s} {units[i]:16s} {row[i]}")
 
 

@@ -9,6 +9,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mcm_b200 import synth  # noqa: E402
+if os.environ.get("AB_LIB"):          # an A/B build made by mcm_b200.build.build_variant
+    from mcm_b200 import _lib
+    _lib.use_library(os.environ["AB_LIB"])
 from mcm_b200.engine import McmEngine  # noqa: E402
 
 cfg = synth.CFGS["tiny"]
@@ -37,4 +40,4 @@ for K in (768, 3072):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 100
-        print(json.dumps(dict(kind=name, M=M, N=N, K=K, us=us, tflops=2.0 * M * N * K / us / 1e6)), flush=True)
+        print(json.dumps(dict(lib=os.path.basename(os.environ.get("AB_LIB", "default")), kind=name, M=M, N=N, K=K, us=us, tflops=2.0 * M * N * K / us / 1e6)), flush=True)
