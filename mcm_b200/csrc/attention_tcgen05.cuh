@@ -7,43 +7,49 @@
 // the tensor core: every softmax thread computes its row's score against it with 64 FMAs (its q row from the Q
 // tile, the key from a small "x box": the producer also loads rows 256.. of q / k / v, 8 rows x 128 B each, with
 // every item), folds it into the row max / row sum, and adds p_extra * v_extra to the O row while draining it.
-// (Reading q / k / v of that token from global memory instead put ~5 k cycles of load latency on every unit.)  The 256 other keys take the normal path with keys_pad = 256.  Likewise the one
-// QUERY row beyond 256 does not get a (1 / 128 full) third unit: warp 10 computes it with warp-level mma.sync tiles
-// from the K / V tiles already in shared memory, hidden behind the two real units.
+// (Reading q / k / v of that token from global memory instead put ~5 k cycles of load latency on every unit.)
+// The 256 other keys take the normal path with keys_pad = 256.  Likewise the one QUERY row beyond 256 does not
+// get a (1 / 128 full) third unit: warp 10 computes it with warp-level mma.sync tiles from the K / V tiles already
+// in shared memory, hidden behind the two real units.
 //
 // Persistent CTAs (one per SM) walk over (image, head) items; every item is cut into 128-query-row
-// units.  Warp roles:
-//   warp 0      TMA producer: K and V of the item ([keys_pad x 64] fp16 boxes, 128-byte swizzle, 2-stage
-//               ring; 3-D tensor map over [image][token][3 D], so key rows beyond the image's S tokens are zero-filled)
-//               and the Q tile of every unit (3-stage ring), straight out of the fused QKV buffer.
-//   warp 1      MMA issuer (one elected thread):  S = Q K^T   as UMMA 128 x keys_pad x 16 (x4, SS mode),
-//                                                 O = P V     as UMMA 128 x 64 x 16 (x keys_pad/16, TS mode:
-//               P is read from TENSOR MEMORY, V from shared memory as an MN-major operand).
-//   warps 2-9   two softmax groups of 4 warps; group g owns TMEM buffer g (256 columns), one thread per
-//               query row: row max and exp2 in fp32 straight from TMEM (tcgen05.ld), P written back over
-//               the dead S columns as fp16 (tcgen05.st), then O / rowsum -> fp16 -> smem transpose ->
-//               coalesced 128-byte row stores.  While one group runs its softmax the tensor core serves
-//               the other group's QK^T / PV, so the MUFU (exp2) pipe -- the real bound of this kernel:
-//               2 x 128 x keys_pad exponentials per item vs 16 per clock per SM -- stays busy.
-// TMEM map of buffer g (base = g * 256 columns):  S fp32 [0, keys_pad)  ->  P fp16 [0, keys_pad/2)
-//                                                 O fp32 [128, 192)  (dead S columns by the time PV runs)
-// Padded keys (>= S) are masked to probability 0; padded query rows are computed and never stored.
-// Sequences of at most 64 tokens (ViT-B/32: 50) would fill 39 % of a 128-row unit: there a unit carries TWO items (pair_mode).
+// units; unit u of a CTA lives in TMEM score buffer u & 1 and is served by softmax group u & 1.  Warp roles (12 warps):
+//   warp 0      TMA producer: K and V tiles of the item ([keys_pad x 64] fp16 boxes, 128-byte swizzle, 2 stages, K and V
+//               with their own full / empty barrier pairs; 3-D tensor map over [image][token][3 D], so key rows beyond the
+//               image's S tokens arrive as zeros) and the Q tile of every unit (3-stage ring), straight out of the fused
+//               QKV buffer.  Issue order per item: K, Q of the first unit, V (+ x box), the other Q tiles.
+//   warps 1, 11 MMA issuers, one elected thread per TMEM buffer (warp 1: buffer 0, warp 11: buffer 1):
+//                 S = Q K^T  as UMMA 128 x keys_pad x 16 (x4, SS mode),
+//                 O = P V    as UMMA 128 x 64 x 16 (x keys_pad/16, TS mode: P is read from TENSOR MEMORY, V from shared
+//               memory as an MN-major operand), issued in up to three parts of 64 keys while the exp2 pass is still
+//               producing the later columns (one mbarrier per part, see atc_two_pass).  Each thread blocks only on its own
+//               buffer's barriers; the tensor core executes the two streams in arrival order.
+//   warps 2-9   two softmax groups of 4 warps, one thread per query row: row max and exp2 in fp32 straight from TMEM
+//               (tcgen05.ld), P written back over the dead S columns as fp16 (tcgen05.st), then O / rowsum -> fp16 -> the
+//               SWIZZLE_128B image of a [32 rows x 64] box in shared memory -> ONE 3-D TMA bulk store per warp and unit (rows
+//               beyond the image's S tokens are clipped by the TMA unit).  The loops over the 32-key chunks have compile-time
+//               trip counts for the two production shapes (template NFULL / REM16).
+//   warp 10     tail rows (query rows >= 256, ViT-L/14 only) on mma.sync tiles.
+// TMEM map.  keys_pad <= 224 (ViT-B/16: 208): S / P of buffer g at columns g * keys_pad, ONE O tile shared by the two
+// groups at 2 * keys_pad (64 columns): P.V writes outside the score buffer, so the next-but-one Q K^T is issued right behind
+// P.V and the group drains O while the tensor core already computes its next S.  Wider rows (ViT-L/14: 256) leave no room: O
+// stays inside each 256-column buffer (columns 128..191, dead by the time P.V runs) and P.V is issued in one piece.
+// Padded keys (>= S) get probability 0; padded query rows are computed and never stored; a warp whose 32 rows are all padding
+// skips both passes.  Sequences of at most 64 tokens (ViT-B/32: 50) put TWO items into a unit (pair_mode).
 //
-// Measured (clock64 phase trace of one CTA, ViT-B/16 shape, tools/attn_sweep.py with the -DMCM_ATC_TRACE
-// build): one unit takes ~7.7 k cycles end to end -- row max 1.4 k, exp2 pass 3.1 k (the warp's own
-// instruction stream, MUFU 53 % busy), and ~3.2 k of hand-offs (barrier hops, issuing 13 P.V UMMAs,
-// draining O) -- with two units in flight per SM (TMEM holds two S buffers).  Tried and rejected: software-
-// pipelined TMEM loads (+13 %), one pass per row with a lazily raised reference maximum (
-// +6 %), two threads per row, one MMA issuer warp per buffer, forcing the two groups out of phase (all +-5 %), and
-// moving the 69 rows beyond the first 128 of ViT-B/16 to four mma.sync warps so that an item needs ONE unit (2.2 x
-// slower: a 16-row mma.sync tile over 208 keys takes one warp ~8 k cycles, five of them per item on four warps).
-// Two more, both neutral or worse although each removes what a model of the kernel says is its bound: O in a TMEM tile
-// outside the score buffers so that the next-but-one Q K^T is issued right behind P.V instead of after the O drain
-// (97.7 vs 97.9 us), and keeping 1 / 2 / 3 of the seven 32-key score chunks in registers between the two softmax
-// passes to relieve the 64 B/clk TMEM read port (245 KB per unit = 3.8 k cycles, the measured unit time): 106 / 112 /
-// 123 us against 103 for the same code keeping none.  96 us per layer call vs 293 us for the
-// mma.sync kernel; the next step is a third unit in flight (split the keys, rescale O in TMEM).
+// Measured (round 2, clock64 phase trace of one CTA with the -DMCM_ATC_TRACE build, profiles/r02_attention_trace.txt;
+// ViT-B/16, b = 512): a group turns a unit around in 5.7 k cycles -- both passes 3.3-3.6 k, wait for the last part of P.V
+// 0.8-0.9 k, O drain + store 0.6 k, wait for the next S 0.75 k -- and the two groups interleave, so the SM finishes a unit
+// every 2.85 k cycles (round 1: 3.9 k).  Eight softmax warps running NOTHING but the two passes need 2.53 k
+// (tools/microbench/softmax_unit.cu); the MUFU bound is 1.66 k.  147 us per launch against 286 us in round 1 and 293 us for
+// the mma.sync kernel.  What got it there, in order of effect: constant-trip loops + bulk stores of O (173 -> 154 us),
+// one issuer thread per buffer + P.V in parts + separate K / V barriers (154 -> 147), index math without integer divisions
+// (179 -> 174), the shared O tile (174 -> 173).  Tried and rejected this round: a cooperative variant with both groups on
+// one unit's two key halves (20-30 % slower: the max / sum exchange through shared memory serialises the groups), one
+// polling issuer thread using mbarrier.test_wait (~150 cycles per probe; 177 us), P.V in four parts (150 us), part of the
+// exponentials on the FMA pipe (ex2_poly below: flat to 12 %, slower beyond).  Round 1's rejected list (software-pipelined
+// TMEM loads, lazy row maximum, two threads per row, score chunks kept in registers between the passes, the 69 rows beyond
+// 128 on mma.sync warps) is in DESIGN.md.
 //
 // qkv: fp16 [b * S, 3 * H * 64]  (row = token; [q | k | v], head h at columns h * 64 of each part)
 // out: fp16 [b * S, H * 64]      (== attn_output.transpose(1,2).reshape(B,S,D), HF:333)
@@ -184,9 +190,12 @@ __device__ __forceinline__ float atc_chunk_max(const uint32_t (&v)[32], int k0, 
 }
 // 2^x for x <= 0 WITHOUT the special-function unit: round-to-nearest split x = j + f (the magic-number add leaves j in the
 // low mantissa bits of r), a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (relative error 7.5e-5, a sixth of the
-// fp16 rounding the probability gets next), and j added into the exponent field.  8 FMA/ALU-pipe instructions against ONE
-// MUFU.EX2 -- but the SM has 16 MUFU lanes per clock against 128 FMA lanes, and the exp2 pass of a softmax warp is paced by
-// its own back-to-back MUFU instructions (8 cycles each per warp); these fill the issue slots in between.
+// fp16 rounding the probability gets next), and j added into the exponent field: 8 FMA/ALU-pipe instructions against ONE
+// MUFU.EX2 (16 lanes per clock and SM against 128 FMA lanes).  MEASURED, round 2 (tools/attn_sweep.py, b = 512, S = 197):
+// 0 / 12 / 25 / 31 / 37 / 50 % of the keys through the polynomial = 145.3 / 144.3 / 146.2 / 149.5 / 153.6 / 158.3 us -- ptxas
+// does interleave the two instruction streams, but the exp2 pass is not paced by the MUFU pipe (math-pipe-throttle stalls:
+// 1 % of the samples; the two groups' passes overlap in time and the SM's MUFU lanes are 58 % busy), so the extra issue
+// slots buy nothing.  Off by default (mask 0); kept as an A/B build switch.
 __device__ __forceinline__ float ex2_poly(float x) {
     x = fmaxf(x, -125.f);                                   // keeps the exponent field positive; 2^-125 rounds to P = 0 anyway
     const float r = x + 12582912.f;                         // 1.5 * 2^23
@@ -198,7 +207,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 // which of the 32 keys of a full chunk take ex2_poly instead of MUFU.EX2 (bit i = key i of the chunk)
 #ifndef MCM_ATC_POLY_MASK
-#define MCM_ATC_POLY_MASK 0x88888888u
+#define MCM_ATC_POLY_MASK 0u
 #endif
 template <int I>
 __device__ __forceinline__ float atc_ex2(float x) {
