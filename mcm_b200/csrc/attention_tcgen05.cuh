@@ -75,6 +75,7 @@ struct AtcParams {
     int pair_mode;           // S <= 64 (ViT-B/32): TWO (image, head) items share a unit -- rows / keys 0..63 item 2w, 64..127
                              // item 2w + 1, keys_pad = 128, a row's probabilities of the other item's keys are zero
     int units_per_item;      // ceil(min(S, 256) / 128)
+    int reverse;             // walk the items from the last image to the first (L2 reuse: start on the rows the QKV GEMM wrote last)
     float inv_H;             // 1 / H (image = item / H without an integer division, see atc_div_h)
     float scale_log2e;       // dh^-0.5 * log2(e)
     op16_t* out;
@@ -368,7 +369,8 @@ __device__ __forceinline__ void atc_producer(const CUtensorMap& tmap_q, const CU
         tma_load_2d(s_q + qs * kAtcQBytes, &tmap_q, &q_full[qs], h * 64, row0 + mt * 128);
         ++uc;
     };
-    for (int item = blockIdx.x; item < n_work; item += gridDim.x, ++ic) {
+    for (int slot = blockIdx.x; slot < n_work; slot += gridDim.x, ++ic) {
+        const int item = p.reverse ? n_work - 1 - slot : slot;
         const int kvs = ic & 1;
         const uint32_t ph = ((ic >> 1) & 1) ^ 1;
         uint8_t* sk = s_kv + kvs * 2 * kv_bytes;
@@ -429,7 +431,8 @@ __device__ __forceinline__ void atc_tail_rows(const AtcParams& p, const AtcSmem&
     const bool row_lane = (lane >> 2) == 0;      // lanes 0..3 hold row 0 of the tile
     uint32_t ic = 0;
     auto lds32 = [](uint32_t a) { uint32_t w; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(a)); return w; };
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+    for (int slot = blockIdx.x; slot < n_items; slot += gridDim.x, ++ic) {
+        const int item = p.reverse ? n_items - 1 - slot : slot;
         const int img = atc_div_h(item, p.inv_H), h = item - img * p.H;
         const int kvs = ic & 1;
         const uint32_t sk = smem_u32(s_kv + kvs * 2 * kv_bytes);
@@ -717,7 +720,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const uint32_t j = u >> 1;
             const uint32_t iu = atc_unit_item(u, upi);
             const int mt = static_cast<int>(u - iu * upi);
-            const int work = static_cast<int>(blockIdx.x) + static_cast<int>(iu) * static_cast<int>(gridDim.x);
+            const int slot = static_cast<int>(blockIdx.x) + static_cast<int>(iu) * static_cast<int>(gridDim.x);
+            const int work = p.reverse ? n_work - 1 - slot : slot;
             const int item = pair ? 2 * work + half : work;
             const int img = atc_div_h(item, p.inv_H), h = item - img * p.H;
             const int wrow0 = pair ? (quad & 1) * 32 : mt * 128 + quad * 32;       // first query row (within the image) of this warp

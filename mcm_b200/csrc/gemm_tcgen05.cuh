@@ -41,6 +41,7 @@ struct GemmParams {
     int n_tiles;        // N / BLOCK_N
     int k_blocks;       // K / 64
     int m_valid;        // rows >= m_valid are computed but never stored
+    int m_reverse;      // walk the row blocks from the last to the first (L2 reuse along a producer -> consumer chain)
     int ldo;            // leading dimension (elements) of out / resid / out16
     const float* bias;  // [N] (unused for EPI_POS_F32); the folded d vector for EPI_LN_*
     void* out;          // fp16 or fp32

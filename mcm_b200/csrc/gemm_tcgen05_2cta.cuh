@@ -91,6 +91,14 @@ struct Gemm2Smem {
 };
 
 // ---- cluster / 2-CTA PTX ----
+// tile index -> (row block, column block).  Tiles are walked row-block-major; with p.m_reverse the row blocks run from the
+// LAST to the first, so that a GEMM whose producer walked upwards starts on the rows that are still in L2 (engine.cu alternates
+// the direction along the qkv -> attention -> out_proj -> fc1 -> fc2 chain).
+__device__ __forceinline__ void gemm2_tile_pos(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+    m_blk = tile / p.n_tiles;
+    n_blk = tile - m_blk * p.n_tiles;
+    if (p.m_reverse) m_blk = p.m_tiles - 1 - m_blk;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -520,8 +528,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile / p.n_tiles;
-                const int n_blk = tile - m_blk * p.n_tiles;
+                int m_blk, n_blk;
+                gemm2_tile_pos(p, tile, m_blk, n_blk);
                 const int a_row = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM;
                 const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
                 for (int kt = 0; kt < k_total; ++kt) {
@@ -603,8 +611,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             const uint32_t stg = smem_u32(staging + ew * (kSliceCols * 64));
 #endif
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile / p.n_tiles;
-                const int n_blk = tile - m_blk * p.n_tiles;
+                int m_blk, n_blk;
+                gemm2_tile_pos(p, tile, m_blk, n_blk);
                 const int m_base = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
                 const int col_base = n_blk * BLOCK_N + slice * kSliceCols;
                 float rstd = 1.f, nmr = 0.f;
@@ -668,8 +676,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             // chunk g of this warp -> (global row of the warp's first row, first column)
             auto chunk_pos = [&](int g, int& m0, int& c0) {
                 const int tile = cluster_id + (g / kChunks) * num_clusters;
-                const int m_blk = tile / p.n_tiles;
-                const int n_blk = tile - m_blk * p.n_tiles;
+                int m_blk, n_blk;
+                gemm2_tile_pos(p, tile, m_blk, n_blk);
                 m0 = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
                 c0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + (g % kChunks) * 32;
             };
@@ -775,8 +783,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             const int n_chunks = my_tiles * kChunks;
             auto chunk_pos = [&](int g, int& m0, int& c0) {
                 const int tile = cluster_id + (g / kChunks) * num_clusters;
-                const int m_blk = tile / p.n_tiles;
-                const int n_blk = tile - m_blk * p.n_tiles;
+                int m_blk, n_blk;
+                gemm2_tile_pos(p, tile, m_blk, n_blk);
                 m0 = m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
                 c0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + (g % kChunks) * 32;
             };
@@ -858,8 +866,8 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             static_assert(kChunks % 2 == 0, "the side-value double buffer alternates per chunk");
             const uint32_t stg = smem_u32(staging + ew * 4096);
             auto tile_rows = [&](int tile, int& n_blk) {
-                const int m_blk = tile / p.n_tiles;
-                n_blk = tile - m_blk * p.n_tiles;
+                int m_blk;
+                gemm2_tile_pos(p, tile, m_blk, n_blk);
                 return m_blk * kGemm2TileM + static_cast<int>(rank) * kGemmBlockM + quad * 32;
             };
             float4 side[2][8];

@@ -3,6 +3,8 @@
 import pytest
 import torch
 
+from helpers import report
+
 pytestmark = pytest.mark.gpu
 
 
@@ -24,6 +26,7 @@ def test_attention(engine_factory, b, S, H):
     ref = ref.transpose(1, 2)
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
+    report("attention", dict(case="random", b=b, S=S, H=H, max_abs_err=err, ref_absmax=ref.abs().max().item()))
     assert err <= 3e-2, err     # fp16 probabilities / fp16 output rounding
 
 
@@ -47,6 +50,7 @@ def test_attention_extra_key_dominates(engine_factory):
     torch.cuda.synchronize()
     assert prob[..., 256].max().item() > 0.5                 # the extra key really matters in this case
     err = (out - ref).abs().max().item()
+    report("attention", dict(case="extra_key", b=b, S=S, H=H, max_abs_err=err, ref_absmax=ref.abs().max().item()))
     assert err <= 3e-2, err
 
 
@@ -71,4 +75,5 @@ def test_attention_late_maximum(engine_factory, S):
     ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2)
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
+    report("attention", dict(case="late_max", b=b, S=S, H=H, max_abs_err=err, ref_absmax=ref.abs().max().item()))
     assert err <= 3e-2, err

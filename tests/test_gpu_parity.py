@@ -93,8 +93,8 @@ def test_image_features_match_oracle(engine_factory, cfg_name, b):
     cos = torch.nn.functional.cosine_similarity(got, ref, dim=1).min().item()
     report("features", dict(cfg=cfg_name, rel_err=rel, min_cos=cos))
     assert got.shape == (b, cfg.proj) and got.dtype == torch.float32
-    assert rel <= 3e-2, rel
-    assert cos >= 0.9995, cos
+    assert rel <= 3e-3, rel            # fp16 operands: measured 6e-4 .. 1.1e-3 (the split mode: tests/test_gpu_precision.py)
+    assert cos >= 0.99999, cos
 
 
 @pytest.mark.parametrize("noise,precision,fpr_tol", [(0.8, "fp16", 2.5e-3), (0.68, "fp16", 2.5e-3), (0.8, "split", 5e-4), (0.68, "split", 5e-4)])
@@ -182,7 +182,7 @@ def test_uint8_ingest_patch_geometries(engine_factory, cfg_name):
         ref = O.image_features(f32, sd, cfg)
     rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
     report("features_u8", dict(cfg=cfg_name, rel_err=rel))
-    assert rel <= 3e-2, rel
+    assert rel <= 3e-3, rel
 
 
 @pytest.mark.parametrize("cfg_name", ["small", "ViT-B/16"])
@@ -209,6 +209,6 @@ def test_features_with_outlier_channels(cfg_name):
         ratio = float(hidden.abs().max() / hidden.std())
         report("features_outliers", dict(cfg=cfg_name, rel_err=rel, max_over_std=ratio))
         assert ratio > 10           # the stream really carries outliers
-        assert rel <= 3e-2, rel
+        assert rel <= 3e-3, rel     # measured 1.3e-4 / 2.8e-4
     finally:
         eng.close()

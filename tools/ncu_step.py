@@ -15,9 +15,12 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--model", default="ViT-B/16")
 ap.add_argument("--K", type=int, default=1000)
 ap.add_argument("--no-shortcut", action="store_true")
+ap.add_argument("--lib", default="", help="an A/B build made by mcm_b200.build.build_variant")
 a = ap.parse_args()
 
-from mcm_b200 import synth
+from mcm_b200 import _lib, synth
+if a.lib:
+    _lib.use_library(os.path.abspath(a.lib))
 from mcm_b200.engine import McmEngine
 
 cfg = synth.CFGS[a.model]
