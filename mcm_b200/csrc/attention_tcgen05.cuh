@@ -629,30 +629,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (elect_one()) atc_producer(tmap_q, tmap_kv, tmap_x, p, sm);
     } else if (warp == 1 || warp == 11) {
         if (elect_one()) {
-            // ===== MMA issuers: one thread per TMEM buffer (warp 1: buffer 0, warp 11: buffer 1) =====
-            // Buffer b carries the units b, b + 2, ...:  Q K^T -> [softmax] -> P.V in nparts pieces -> [drain].  Each thread
+            // ===== MMA issuers =====
+            // Unit u lives in TMEM buffer u & 1:  Q K^T -> [softmax] -> P.V in nparts pieces -> [drain].
+            // Shared O tile (keys_pad <= 224): one thread per buffer (warp 1: units 0, 2, ..; warp 11: units 1, 3, ..).  Each
             // blocks only on ITS buffer's barriers, so a group never waits behind the other group's hand-offs (round 1's
             // single in-order thread: ~1.9 k idle cycles per unit, profiles/r02_attention_trace.txt), and the hardware-assisted
             // try_wait wakes it ~60 cycles after the arrive (polling both buffers with test_wait from one thread cost ~150
             // cycles per probe and was slower than the in-order loop).  The tensor core executes the two streams in the order
             // it receives them; every dependency between them goes through a barrier: the shared O tile (s_free of the other
             // group), the K / V stages (k_empty / v_empty count one commit per unit of the item).
-            const int buf = warp == 1 ? 0 : 1;
+            // O inside the score buffers (ViT-L/14): the next Q K^T of a buffer has to wait for the drain anyway, there is
+            // nothing for a second thread to overlap, and ONE in-order thread (warp 1) measured 6 % faster (80.7 vs 86 us).
+            const uint32_t first = (shared_o && warp == 11) ? 1u : 0u;
+            const uint32_t stride = shared_o ? 2u : 1u;
             const int my_items = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-            const uint32_t n_units = static_cast<uint32_t>(my_items * upi);
+            const uint32_t n_units = (!shared_o && warp == 11) ? 0u : static_cast<uint32_t>(my_items * upi);
             const uint32_t idesc_qk = make_idesc_f16(128, static_cast<uint32_t>(p.keys_pad));
             const uint32_t idesc_pv = make_idesc_f16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
             const int ksteps = p.keys_pad >> 4;
-            const uint32_t a_tmem = tmem_base + buf * buf_stride;                     // S, then P, of this buffer
-            const uint32_t o_tmem = shared_o ? tmem_base + 2 * buf_stride : a_tmem + 128;
             auto issue_qk = [&](uint32_t v) {
                 const uint32_t iv = atc_unit_item(v, upi);                      // CTA-local item index of unit v
-                const int kvs = iv & 1, qs = v % kAtcQStages;
+                const int kvs = iv & 1, qs = v % kAtcQStages, buf = v & 1;
                 mbar_wait(&k_full[kvs], (iv >> 1) & 1);
                 mbar_wait(&q_full[qs], (v / kAtcQStages) & 1);
                 tcgen05_fence_after();
                 const uint64_t adesc = make_smem_desc_sw128(smem_u32(s_q + qs * kAtcQBytes), 16, 1024);
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes), 16, 1024);
+                const uint32_t a_tmem = tmem_base + buf * buf_stride;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16(a_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
                 umma_commit(&q_empty[qs]);
@@ -660,10 +663,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 umma_commit(&k_empty[kvs]);               // this unit is done with the item's K tile
                 ATC_TRACE(0, v, 0);                       // QK^T of unit v issued
             };
-            if (static_cast<uint32_t>(buf) < n_units) issue_qk(buf);
-            for (uint32_t u = buf; u < n_units; u += 2) {
+            for (uint32_t v = first; v < 2u && v < n_units; v += stride) issue_qk(v);
+            for (uint32_t u = first; u < n_units; u += stride) {
                 const uint32_t iu = atc_unit_item(u, upi);
-                const int kvs = iu & 1;
+                const int kvs = iu & 1, buf = u & 1;
+                const uint32_t a_tmem = tmem_base + buf * buf_stride;                     // S, then P, of this unit's buffer
+                const uint32_t o_tmem = shared_o ? tmem_base + 2 * buf_stride : a_tmem + 128;
                 // V tile: [keys][64 dh] rows of 128 B = MN-major B operand; 16 keys (one UMMA K) = 2048 B
                 const uint64_t vdesc = make_smem_desc_sw128(smem_u32(s_kv + kvs * 2 * kv_bytes + kv_bytes), 1024, 1024);
                 for (int part = 0; part < nparts; ++part) {
@@ -686,7 +691,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         ATC_TRACE(0, u, 3);
                         tcgen05_fence_after();
                     }
-                    issue_qk(u + 2);      // the tensor core runs it behind P.V(u) of this thread, the last reader of P(u)
+                    issue_qk(u + 2);      // the tensor core runs it behind P.V(u), the last reader of P(u)
                 }
             }
         }
