@@ -27,7 +27,7 @@ def test_attention(engine_factory, b, S, H):
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     report("attention", dict(case="random", b=b, S=S, H=H, max_abs_err=err, ref_absmax=ref.abs().max().item()))
-    assert err <= 3e-2, err     # fp16 probabilities / fp16 output rounding
+    assert err <= 4e-3, err     # fp16 probabilities / fp16 output rounding: measured <= 1.1e-3 on outputs up to 3.8
 
 
 def test_attention_extra_key_dominates(engine_factory):
@@ -51,7 +51,7 @@ def test_attention_extra_key_dominates(engine_factory):
     assert prob[..., 256].max().item() > 0.5                 # the extra key really matters in this case
     err = (out - ref).abs().max().item()
     report("attention", dict(case="extra_key", b=b, S=S, H=H, max_abs_err=err, ref_absmax=ref.abs().max().item()))
-    assert err <= 3e-2, err
+    assert err <= 8e-3, err     # measured 2.0e-3 on outputs up to 7.7
 
 
 @pytest.mark.parametrize("S", [197, 257, 50])
@@ -76,4 +76,4 @@ def test_attention_late_maximum(engine_factory, S):
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     report("attention", dict(case="late_max", b=b, S=S, H=H, max_abs_err=err, ref_absmax=ref.abs().max().item()))
-    assert err <= 3e-2, err
+    assert err <= 4e-3, err     # measured 1e-6: the row is one key
