@@ -47,7 +47,10 @@
 // (179 -> 174), the shared O tile (174 -> 173).  Tried and rejected this round: a cooperative variant with both groups on
 // one unit's two key halves (20-30 % slower: the max / sum exchange through shared memory serialises the groups), one
 // polling issuer thread using mbarrier.test_wait (~150 cycles per probe; 177 us), P.V in four parts (150 us), part of the
-// exponentials on the FMA pipe (ex2_poly below: flat to 12 %, slower beyond).  Round 1's rejected list (software-pipelined
+// exponentials on the FMA pipe (ex2_poly below: flat to 12 %, slower beyond), and -- once more, after round 1 -- two softmax
+// warps per (group, quadrant) splitting the key chunks of their 32 rows (20 warps, 96 registers, row max / sum exchanged
+// through shared memory, each half packing its P at the start of its own score columns): 167 vs 155 us on the same box,
+// ViT-L/14 103 vs 85 us.  Four warps per sub-partition do not buy what two cannot hide; the exchange barriers cost more.  Round 1's rejected list (software-pipelined
 // TMEM loads, lazy row maximum, two threads per row, score chunks kept in registers between the passes, the 69 rows beyond
 // 128 on mma.sync warps) is in DESIGN.md.
 //
