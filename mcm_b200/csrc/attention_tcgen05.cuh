@@ -46,7 +46,8 @@
 // one issuer thread per buffer + P.V in parts + separate K / V barriers (154 -> 147), index math without integer divisions
 // (179 -> 174), the shared O tile (174 -> 173).  Tried and rejected this round: a cooperative variant with both groups on
 // one unit's two key halves (20-30 % slower: the max / sum exchange through shared memory serialises the groups), one
-// polling issuer thread using mbarrier.test_wait (~150 cycles per probe; 177 us), P.V in four parts (150 us), part of the
+// polling issuer thread using mbarrier.test_wait (~150 cycles per probe; 177 us; with one thread per buffer polling its
+// one barrier: 145.9 vs 145.4 us, no difference), P.V in four parts (150 us), part of the
 // exponentials on the FMA pipe (ex2_poly below: flat to 12 %, slower beyond), and -- once more, after round 1 -- two softmax
 // warps per (group, quadrant) splitting the key chunks of their 32 rows (20 warps, 96 registers, row max / sum exchanged
 // through shared memory, each half packing its P at the start of its own score columns): 167 vs 155 us on the same box,
@@ -681,10 +682,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     }
                     mbar_wait(&p_part[kAtcMaxParts * buf + part], (u >> 1) & 1);
                     if (part == 0) ATC_TRACE(0, u, 1);            // first keys of P of unit u ready
+                    if (part + 1 == nparts) ATC_TRACE(0, u, 4);   // last part of P of unit u ready
                     tcgen05_fence_after();
                     const int k0 = 4 * part, k1 = part + 1 == nparts ? ksteps : 4 * (part + 1);
                     for (int k = k0; k < k1; ++k) umma_f16_ts(o_tmem, a_tmem + 8 * k, vdesc + 128ull * k, idesc_pv, k != 0);
                 }
+                ATC_TRACE(0, u, 5);                       // last P.V instruction of unit u issued
                 umma_commit(&o_full[buf]);
                 umma_commit(&v_empty[kvs]);               // this unit is done with the item's V tile
                 ATC_TRACE(0, u, 2);                       // P.V of unit u issued
@@ -769,6 +772,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tcgen05_fence_before();
             __syncwarp();
             if (quad == 2 && lane == 0) ATC_TRACE(1 + g, u, 2);       // pass 2 done
+            if (quad != 2 && lane == 0) ATC_TRACE(1 + g, u, 5 + (quad == 3 ? 2 : quad));   // ... on the other three quadrants (events 5, 6, 7)
             if (lane == 0) {
                 if (!warp_valid)      // a warp without rows still owes the barriers of the earlier parts its arrival
                     for (int i = 0; i + 1 < nparts; ++i) mbar_arrive(&p_part[kAtcMaxParts * g + i]);

@@ -649,7 +649,7 @@ int launch_attention(McmHandle* h, const CUtensorMap& tq, const CUtensorMap& tkv
             for (int r = 0; r < 3; ++r)
                 for (int u = 0; u < 16; ++u) {
                     printf("ATC_TRACE %s unit %2d:", names[r], u);
-                    for (int e = 0; e < 5; ++e) printf(" %8lld", t[(r * 16 + u) * 8 + e] ? t[(r * 16 + u) * 8 + e] - t0 : -1);
+                    for (int e = 0; e < 8; ++e) printf(" %8lld", t[(r * 16 + u) * 8 + e] ? t[(r * 16 + u) * 8 + e] - t0 : -1);
                     printf("\n");
                 }
             fflush(stdout);
