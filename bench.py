@@ -160,6 +160,12 @@ def cpu_as_shipped_rates(cfg, sd, K):
     return out
 
 
+def workload_name(model, K):
+    """config.workload of BOTH arms (the driver compares them)."""
+    return (f"CLIP {model} image encoder + MCM scoring, K={K} prompt bank (BASELINE "
+            f"configs[{3 if model == 'ViT-L/14' else 2}] shape), synthetic 224x224 fp32 stream, random-init weights")
+
+
 def run_reference(args, rank):
     """`--impl reference`: the reference's own CPU path for the same metric/config (rank 0 only)."""
     if rank != 0:
@@ -185,8 +191,10 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"CLIP {args.model} image encoder + MCM scoring, K={args.K} prompt bank, "
-                                   f"synthetic 224x224 stream", "batch_per_step": per_step, "device": "host CPU"},
+            "config": {"workload": workload_name(args.model, args.K), "batch_per_gpu": args.batch,
+                       "global_batch": args.batch * max(1, args.gpus), "parallelism": f"dp{max(1, args.gpus)}",
+                       "reference_step": f"{per_step} images of that workload per step (bounded CPU sample, same per-image work)",
+                       "device": "host CPU"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} steps x {per_step} images, torch-CPU fp32 oracle port of "
                                        f"utils/detection_util.py:209-249 + HF CLIP (bank pre-encoded), {cores} threads"},
@@ -428,9 +436,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "step_ms": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": f"CLIP {args.model} image encoder + MCM scoring, K={K} prompt bank (BASELINE "
-                                   f"configs[{3 if args.model == 'ViT-L/14' else 2}] shape), synthetic 224x224 fp32 stream, "
-                                   f"random-init weights",
+            "config": {"workload": workload_name(args.model, K),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": f"resident input pool {len(pool)} x {B * 3 * 224 * 224 * 4 / 1e6:.0f} MB rotates (> 126 MB L2)",
                        "precision": "fp16 tensor-core operands, fp32 accumulation / LayerNorm statistics / softmax / tail, residual "
