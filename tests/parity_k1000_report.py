@@ -4,7 +4,7 @@ restatement run on the same GPU (TF32 off).  Prints one JSON line per (config, n
 score error, AUROC / FPR95 of both sides and their differences, and keeps the raw score vectors under
 gpurun_out/ for offline analysis.  The same harness is what tests/test_gpu_parity_k1000.py asserts on.
 
-    python tools/parity_k1000.py --cfg ViT-B/16 --n-id 5000 --n-ood 10000 --noise 0.8 --precision 0 1
+    python tests/parity_k1000_report.py --cfg ViT-B/16 --n-id 5000 --n-ood 10000 --noise 0.8 --precision 0 1
 """
 import argparse
 import json
