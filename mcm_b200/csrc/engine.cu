@@ -470,7 +470,7 @@ int launch_gemm(McmHandle* h, int prof_kind, const CUtensorMap& ta, const CUtens
         if (rc) return rc;
         if ((rc = make_tmap_epi(h, &tout16, ln.out16_lo, M, N, false, 32))) return rc;
     } else if (f16_out && MCM_GEMM_F16_TMA_STORE) {
-        int rc = make_tmap_epi(h, &tout, out, M, N, false, bn / 4);
+        int rc = make_tmap_epi(h, &tout, out, M, N, false, (MCM_GEMM_F16_CHUNK_STORE && bn == 256) ? 32 : bn / 4);
         if (rc) return rc;
     } else if (epi == EPI_BIAS_RESID_F32_LN_TMA) {
         int rc = make_tmap_epi(h, &tout, out, M, N, true, 32);

@@ -35,6 +35,12 @@ constexpr int kGemm2TileM = 256;     // rows per cluster tile (128 per CTA)
 #define MCM_GEMM_F16_TMA_STORE 1   // 1: fp16 outputs leave through a shared-memory staging tile + TMA bulk stores (default)
                                    // 0: 32-byte row-per-thread stores straight from registers (A/B builds; measured slower)
 #endif
+#ifndef MCM_GEMM_F16_CHUNK_STORE
+#define MCM_GEMM_F16_CHUNK_STORE 1 // 1 (default): BLOCK_N = 256 fp16 outputs leave as TWO 32-column bulk stores per warp and tile through a
+                                   //    2 KB staging tile -- 32 KB of staging instead of 64 KB (one more ring stage), and the first half of
+                                   //    a warp's output is on its way while the second is still being computed
+                                   // 0: one 64-column store per warp and tile (round 1 / early round 2; A/B builds)
+#endif
 #ifndef MCM_RESID_BUFS
 #define MCM_RESID_BUFS 2
 #endif
@@ -68,7 +74,8 @@ struct EpiTraits {
 
 // Shared memory: operand ring + epilogue staging + barriers.  What the epilogue stages decides how many
 // ring stages are left of the 227 KB:
-//   fp16 outputs          16 warps x (32 rows x 128 B) = 64 KB : one TMA bulk store per warp and tile
+//   fp16 outputs          16 warps x (32 rows x 64 B) = 32 KB : one TMA bulk store per warp and 32-column chunk
+//                         [MCM_GEMM_F16_CHUNK_STORE=0: 16 warps x (32 rows x 128 B) = 64 KB, one store per warp and tile]
 //                         [MCM_GEMM_F16_TMA_STORE=0: none, 32-byte row-per-thread stores straight from registers]
 //   fp32, LSU             8 warps x (32 rows x 128 B)  = 32 KB : transpose tile (EPI_BIAS_RESID_F32, EPI_POS_F32, ..._LN)
 //   fp32 + fp16, TMA      8 warps x (2 x 4 KB residual in / fp32 out + 2 KB fp16 out) = 80 KB  (EPI_BIAS_RESID_F32_LN_TMA)
@@ -78,7 +85,8 @@ struct Gemm2Smem {
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;          // 128 x 64 fp16
     static constexpr int kBBytes = (BLOCK_N / 2) * kGemmBlockK * 2;        // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagingBytes = T::kF16 ? (MCM_GEMM_F16_TMA_STORE ? 16 * (BLOCK_N / 4) * 64 : 0)
+    static constexpr bool kChunkStore = MCM_GEMM_F16_CHUNK_STORE && T::kF16 && BLOCK_N == 256;
+    static constexpr int kStagingBytes = T::kF16 ? (MCM_GEMM_F16_TMA_STORE ? (kChunkStore ? 16 * 2048 : 16 * (BLOCK_N / 4) * 64) : 0)
                                          : T::kTmaResid ? 8 * kResidWarpBytes
                                          : T::kTmaResidH2 ? 8 * kResidH2Bufs * 4096 : 32 * 1024;
     static constexpr int kBarrierBytes = 512;
@@ -392,9 +400,14 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16_direct(const GemmParams
 }
 
 // The same slice through a staging tile + TMA (MCM_GEMM_F16_TMA_STORE builds): the packed rows are
-// written into the warp's staging tile in the TMA swizzle layout of the output box (128-byte rows / SWIZZLE_128B
-// for 64-column slices, 64-byte rows / SWIZZLE_64B for 32-column slices -- conflict-free for a row-per-thread
-// writer) and leave as ONE bulk store per tile; rows beyond the tensor are clipped by the TMA unit.
+// written into the warp's staging tile in the TMA swizzle layout of the output box (64-byte rows / SWIZZLE_64B for
+// 32-column boxes -- conflict-free for a row-per-thread writer) and leave as one bulk store per 32-column chunk; rows
+// beyond the tensor are clipped by the TMA unit.  (MCM_GEMM_F16_CHUNK_STORE=0: 128-byte rows / SWIZZLE_128B, ONE
+// 64-column store per warp and tile.)  Measured, round 2, clock64 trace builds, K = 768 projections at batch 512, cycles
+// the MMA issuer needs per 256 x 256 tile: no global stores 6.16 k | one store per tile 7.49 k | one per chunk 6.57 k
+// (q/k/v), 6.81 k (fc1: the quick_gelu epilogue itself is the longer side now).  In TIME the gain is 3-5 %, not 12 %:
+// the GPU sits at its power cap during these kernels (SM clock ~1.0-1.1 GHz), and cycles the tensor pipe no longer
+// idles are paid for with clock (profiles/r02_gemm_ring_experiments.txt).
 template <int EPI, int BLOCK_N, bool SPLIT>
 __device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, const CUtensorMap* tmap_out, uint32_t stg,
                                                          uint32_t t_addr, int m_base, int col0, int lane, float rstd, float nmr,
@@ -418,6 +431,23 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, co
                 stg_256(orow + 16, pkl + 8);
             }
         }
+        if constexpr (kChunks == 2 && MCM_GEMM_F16_CHUNK_STORE) {
+            // one 32-column chunk at a time through a 2 KB tile (64-byte rows, SWIZZLE_64B); the previous chunk's store has had
+            // this chunk's math to read the tile
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            const uint32_t srow = stg + lane * 64;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4)
+                sts_v4u(srow + ((s4 ^ ((lane >> 1) & 3)) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !MCM_DBG_SKIP(p, 1)) {
+                tma_store_2d(tmap_out, stg, col0 + c * 32, m_base);
+                tma_store_commit();
+            }
+            continue;
+        }
         if (c == 0) {   // the previous tile's store must have read the staging tile (issued a whole main loop ago)
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -434,6 +464,7 @@ __device__ __forceinline__ void gemm2_epilogue_slice_f16(const GemmParams& p, co
                 sts_v4u(srow + ((s4 ^ ((lane >> 1) & 3)) << 4), make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]));
         }
     }
+    if constexpr (kChunks == 2 && MCM_GEMM_F16_CHUNK_STORE) return;   // every chunk went out on its own
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && !MCM_DBG_SKIP(p, 1)) {
@@ -608,7 +639,7 @@ gemm_f16_tn_cta2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             const int slice = ew >> 2;                  // which quarter of the tile's columns this warp drains
             constexpr int kSliceCols = BLOCK_N / 4;
 #if MCM_GEMM_F16_TMA_STORE
-            const uint32_t stg = smem_u32(staging + ew * (kSliceCols * 64));
+            const uint32_t stg = smem_u32(staging + ew * (L::kChunkStore ? 2048 : kSliceCols * 64));
 #endif
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 int m_blk, n_blk;

@@ -14,7 +14,7 @@ from mcm_b200 import synth  # noqa: E402
 from mcm_b200.engine import McmEngine  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out", "gemm_sweep.jsonl")
-M = 50432
+M = int(os.environ.get("SWEEP_M", "50432"))
 CASES = [(768, 64, 0), (768, 64, 1), (768, 64, 2), (3072, 64, 0), (3072, 64, 1),
          (768, 768, 0), (768, 768, 2), (768, 3072, 0), (768, 3072, 2), (768, 6144, 0), (256, 6144, 0),
          (2304, 768, 0), (3072, 768, 0), (3072, 768, 1), (3072, 1536, 0)]
@@ -22,6 +22,9 @@ CASES = [(768, 64, 0), (768, 64, 1), (768, 64, 2), (3072, 64, 0), (3072, 64, 1),
 if os.environ.get("SWEEP_CASES"):   # e.g. "3072,768,0;768,768,6"
     CASES = [tuple(int(v) for v in c.split(",")) for c in os.environ["SWEEP_CASES"].split(";")]
 TAG = os.environ.get("SWEEP_TAG", "")
+if os.environ.get("SWEEP_LIB"):     # an A/B build made by mcm_b200.build.build_variant
+    from mcm_b200 import _lib
+    _lib.use_library(os.path.abspath(os.environ["SWEEP_LIB"]))
 cfg = synth.CFGS["tiny"]
 eng = McmEngine.from_state_dict(synth.synth_vision_state_dict(cfg, 5), cfg, max_batch=4)
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
