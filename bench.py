@@ -82,8 +82,34 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.inst = []          # NVML instantaneous board power (W), every 10 ms: nvidia-smi's power.draw is a ~1 s average,
+        self._nvml_stop = False  # far longer than the timed region
+        self._nvml_h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml_h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            pass
+
+    def _nvml(self):
+        if self._nvml_h is None:
+            return
+        try:
+            import pynvml
+            h = self._nvml_h
+            while not self._nvml_stop:
+                v = pynvml.nvmlDeviceGetFieldValues(h, [pynvml.NVML_FI_DEV_POWER_INSTANT])[0]
+                if v.nvmlReturn != 0:
+                    return
+                self.inst.append(v.value.uiVal / 1000.0)
+                time.sleep(0.01)
+        except Exception:
+            return
 
     def start(self):
+        self.nvml_thread = threading.Thread(target=self._nvml, daemon=True)
+        self.nvml_thread.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -98,6 +124,7 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        self._nvml_stop = True
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -116,8 +143,12 @@ class ClockSampler:
                         reasons.add(nm)
             except (ValueError, IndexError):
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.inst:     # samples under load only (the thread also sees the idle moments around the region)
+            load = [p for p in self.inst if p > 0.5 * max(self.inst)]
+            out["power_w_instant"] = {"mean_under_load": float(np.mean(load)), "max": float(max(self.inst)), "samples": len(load)}
+        return out
 
 
 def cpu_reference_rate(cfg, sd, bank, n_images, repeats=1):
@@ -449,6 +480,10 @@ def main():
                           "note": "same call with decoded uint8 HWC pixels (mcm_score_stream_host_u8): ToTensor + Normalize on the device"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "energy": ({"joule_per_image": clocks["power_w_instant"]["mean_under_load"] * ms * 1e-3 / (args.steps * B),
+                        "note": "NVML instantaneous board power (mean of the samples under load) x device time of the timed region; "
+                                "the step runs at the board's power limit, see DESIGN.md section 4"}
+                       if clocks and clocks.get("power_w_instant") else None),
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_tn_cta2_kernel (tcgen05 cta_group::2, all GEMM launches of a step)",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_unit": "bytes/step (all GEMM launches)",
