@@ -137,6 +137,8 @@ qkv = (torch.randn(M, 3 * D, device="cuda", generator=g) * 0.5).to(torch.float16
 big = torch.randn(8192, 8192, device="cuda", generator=g).to(torch.bfloat16)
 big2 = torch.randn(8192, 8192, device="cuda", generator=g).to(torch.bfloat16)
 w_fc2_small, w_out_small = w_fc2 * 0.01, w_out * 0.01   # keep the in-place residual loops from growing
+cp_src = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+cp_dst = torch.empty_like(cp_src)
 
 WORK = [
     ("step (ViT-B/16 forward + MCM tail)", lambda: eng.score(x), eng.flops_per_image(1000) * b),
@@ -148,6 +150,8 @@ WORK = [
     ("cuBLAS bf16 8192^3 (torch.matmul)", lambda: torch.matmul(big, big2), 2.0 * 8192 ** 3),
     ("cuBLAS fp16 q/k/v shape, no epilogue (torch.matmul)", lambda: torch.matmul(act, w_qkv.t()), 2.0 * M * 3 * D * D),
     ("cuBLAS fp16 fc2 shape, no epilogue (torch.matmul)", lambda: torch.matmul(hid, w_fc2.t()), 2.0 * M * D * F),
+    # 1 GiB read + 1 GiB written per call: what a DRAM byte costs ("flops" = bytes here: pj_per_flop reads as pJ per byte)
+    ("copy 1 GiB (dst.copy_(src); pj_per_flop = pJ per DRAM byte)", lambda: cp_dst.copy_(cp_src), 2.0 * (1 << 30)),
 ]
 only = [s for s in a.only.split(",") if s]
 for name, fn, fl in WORK:
