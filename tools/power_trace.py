@@ -137,6 +137,10 @@ qkv = (torch.randn(M, 3 * D, device="cuda", generator=g) * 0.5).to(torch.float16
 big = torch.randn(8192, 8192, device="cuda", generator=g).to(torch.bfloat16)
 big2 = torch.randn(8192, 8192, device="cuda", generator=g).to(torch.bfloat16)
 w_fc2_small, w_out_small = w_fc2 * 0.01, w_out * 0.01   # keep the in-place residual loops from growing
+big_h, big2_h = big.to(torch.float16), big2.to(torch.float16)
+zero_b = torch.zeros(8192, 8192, device="cuda", dtype=torch.bfloat16)
+zero_h = torch.zeros(8192, 8192, device="cuda", dtype=torch.float16)
+act_zero = torch.zeros_like(act)
 cp_src = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
 cp_dst = torch.empty_like(cp_src)
 
@@ -150,6 +154,11 @@ WORK = [
     ("cuBLAS bf16 8192^3 (torch.matmul)", lambda: torch.matmul(big, big2), 2.0 * 8192 ** 3),
     ("cuBLAS fp16 q/k/v shape, no epilogue (torch.matmul)", lambda: torch.matmul(act, w_qkv.t()), 2.0 * M * 3 * D * D),
     ("cuBLAS fp16 fc2 shape, no epilogue (torch.matmul)", lambda: torch.matmul(hid, w_fc2.t()), 2.0 * M * D * F),
+    # operand format and operand data: what the tensor pipe's energy depends on
+    ("cuBLAS fp16 8192^3 (torch.matmul)", lambda: torch.matmul(big_h, big2_h), 2.0 * 8192 ** 3),
+    ("cuBLAS bf16 8192^3, all-zero operands", lambda: torch.matmul(zero_b, zero_b), 2.0 * 8192 ** 3),
+    ("cuBLAS fp16 8192^3, all-zero operands", lambda: torch.matmul(zero_h, zero_h), 2.0 * 8192 ** 3),
+    ("gemm q/k/v 2304x768, all-zero A", lambda: eng.dbg_gemm_ln(act_zero, w_qkv, bias_qkv, c_qkv, stats, D), 2.0 * M * 3 * D * D),
     # 1 GiB read + 1 GiB written per call: what a DRAM byte costs ("flops" = bytes here: pj_per_flop reads as pJ per byte)
     ("copy 1 GiB (dst.copy_(src); pj_per_flop = pJ per DRAM byte)", lambda: cp_dst.copy_(cp_src), 2.0 * (1 << 30)),
 ]
