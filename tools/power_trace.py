@@ -29,6 +29,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=3.0)
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--only", default="", help="comma-separated workload names")
+ap.add_argument("--steps-only", default="", help="comma-separated model:precision pairs (e.g. ViT-L/14:fp16,ViT-B/16:split): "
+                "loop only the whole step of each and exit")
 a = ap.parse_args()
 
 pynvml.nvmlInit()
@@ -111,6 +113,20 @@ def run_phase(name, fn, flops, seconds):
     print(json.dumps(rec), flush=True)
     time.sleep(0.5)
 
+
+if a.steps_only:
+    for spec in a.steps_only.split(","):
+        model, prec = spec.split(":")
+        cfg = synth.CFGS[model]
+        bb = a.batch if model != "ViT-L/14" else min(a.batch, 256)
+        eng = McmEngine.from_state_dict(synth.synth_vision_state_dict(cfg, 5), cfg, max_batch=bb)
+        eng.set_text_bank(synth.synth_unit_bank(1000, cfg.proj, 3), already_unit=True)
+        eng.set_precision(prec)
+        xs = torch.randn(bb, 3, 224, 224, device="cuda")
+        run_phase(f"step {model} batch {bb} precision {prec}", lambda: eng.score(xs), eng.flops_per_image(1000) * bb, a.seconds)
+        eng.close()
+        del eng, xs
+    sys.exit(0)
 
 b = a.batch
 cfg = synth.CFGS["ViT-B/16"]
