@@ -34,7 +34,7 @@
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #ifndef MCM_SWEEP_ALTERNATE
-#define MCM_SWEEP_ALTERNATE 0         // 1: alternate the direction the streaming kernels walk the token rows (A/B builds, see forward_tower)
+#define MCM_SWEEP_ALTERNATE 1         // 1 (default): alternate the direction the streaming kernels walk the token rows (see forward_tower); 0: A/B builds
 #endif
 #ifndef MCM_RESID_H2_TMA_MAX_K
 #define MCM_RESID_H2_TMA_MAX_K 1024   // residual-pair GEMMs with K up to this take the all-TMA epilogue (A/B builds: 0 or 4096)
@@ -743,11 +743,14 @@ int forward_tower(McmHandle* h, const void* images, bool u8, int b, cudaStream_t
     pooled->xl = h->xh_lo;
     pooled->stride = static_cast<size_t>(h->S) * D;
     const int ld = static_cast<int>(h->m_pad);
-    // MCM_SWEEP_ALTERNATE = 1: every streaming kernel of the chain qkv -> attention -> out_proj -> fc1 -> fc2 -> qkv ... walks the
-    // token rows in the direction OPPOSITE to its producer's, so it starts on the rows that were written last and are still in
-    // L2.  Measured (round 2, ncu --cache-control none over one step at batch 512): DRAM reads 25.78 -> 24.11 GB per step
-    // (15 .. 50 MB per hand-off stay resident), but the step was 1 - 2 % SLOWER in two back-to-back bench pairs on a
-    // power-capped box (25.8 / 25.7 k vs 26.4 / 26.0 k images/s), so it stays off.
+    // MCM_SWEEP_ALTERNATE = 1 (default): every streaming kernel of the chain qkv -> attention -> out_proj -> fc1 -> fc2 -> qkv ...
+    // walks the token rows in the direction OPPOSITE to its producer's, so it starts on the rows that were written last and are
+    // still in L2.  Measured (round 2, ncu --cache-control none over one step at batch 512): DRAM reads 25.89 -> 24.21 GB per
+    // step (15 .. 50 MB per hand-off stay resident; every other hand-off scheme tried -- persisting access-policy windows,
+    // evict-first loads of dead operands -- made the traffic worse: profiles/r02_l2_handoff_experiment.txt).  At the power cap a
+    // DRAM byte is ~72 pJ, i.e. ~0.6 % of the step's energy.  Bench pairs: -1 .. -2 % in two pairs early in the round (before the
+    // chunk stores), +1 % over five runs on a second box, +2.7 % in three alternating pairs on a third (27.92 / 28.12 / 27.92 vs
+    // 27.52 / 27.12 / 27.13 k images/s with the final kernels).  Results are bit-identical (same digest of the verification stream).
     int dir = 1;
     auto next_dir = [&]() { h->sweep_desc = MCM_SWEEP_ALTERNATE ? dir : 0; dir ^= 1; };
     struct SweepReset { McmHandle* h; ~SweepReset() { h->sweep_desc = 0; } } sweep_reset{h};
