@@ -24,6 +24,9 @@ pre-encoded bank -> softmax/T -> max) over one batch of `--batch` synthetic 224x
   ``mcm_b200.parallel.shard_bounds`` and collated with the path's one all-gather; the line carries the SHA-1 of the
   gathered fp32 scores (identical for N = 1, 2, 4, 8) and whether it equals rank 0's own single-rank pass.
 * ``precision_split``: the same step in the split-fp16 precision mode (the mode in which FPR95 parity is exact).
+* ``clocks`` / ``energy``: nvidia-smi clocks and throttle reasons sampled during the timed region, NVML's instantaneous
+  board power next to them, and joule per image = that power x device time / images: the step runs at the board's power
+  limit from its first kernel to its last, so energy per image is what the throughput follows.
 """
 from __future__ import annotations
 
