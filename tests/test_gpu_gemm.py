@@ -74,8 +74,8 @@ LN_SHAPES = [
     (200, 128, 64, 384),      # ragged M, BLOCK_N = 128 on both sides
     (1576, 768, 768, 2304),   # out_proj -> q/k/v of ViT-B/16
     (197 * 160, 768, 128, 256),   # more tiles than clusters: residual prefetch across tiles
-    (197 * 160, 768, 64, 2304),   # resident-A schedule of the K = 768 projections: a full round of row blocks + the tail runs
-    (197 * 40, 1024, 64, 3072),   # the same with K = 1024 (ViT-L/14: 16 k-blocks, 6 of them resident)
+    (197 * 160, 768, 64, 2304),   # q/k/v shape of ViT-B/16 at 160 images: 15 tiles per cluster, chunk stores, every ring wrap
+    (197 * 40, 1024, 64, 3072),   # the same with K = 1024 (ViT-L/14)
 ]
 
 
